@@ -1,0 +1,161 @@
+"""ctypes binding of include/tractgeom.h.  No fallback: a missing library or device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libtractgeom.so")
+
+N_METRICS = 17
+N_BUNDLE_COLS = 13
+KEEP_LOADER, KEEP_LENGTH, KEEP_BOTH = 1, 2, 3
+F64, F32 = 0, 1
+
+# every symbol include/tractgeom.h declares (tests check the .so exports exactly these)
+EXPORTS = (
+    "tg_abi_version", "tg_last_error", "tg_device_count", "tg_create", "tg_destroy", "tg_synchronize",
+    "tg_stream", "tg_host_alloc", "tg_host_free", "tg_metrics_csr_dev", "tg_bundle_reduce_dev",
+    "tg_metrics_csr_host", "tg_launch_count",
+)
+
+
+class TractGeomError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"tractgeom error {code}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    """dlopen libtractgeom.so and declare the prototypes.  Raises if the library was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m lesion_condition_vae_b200.build` "
+            "(nvcc, sm_100a).  There is no CPU implementation to fall back to.")
+    lib = C.CDLL(LIB_PATH)
+    vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
+    lib.tg_abi_version.restype = i32
+    lib.tg_last_error.restype = C.c_char_p
+    lib.tg_device_count.argtypes = [C.POINTER(i32)]
+    lib.tg_create.argtypes = [i32, C.POINTER(vp)]
+    lib.tg_destroy.argtypes = [vp]
+    lib.tg_synchronize.argtypes = [vp]
+    lib.tg_stream.argtypes = [vp, C.POINTER(vp)]
+    lib.tg_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+    lib.tg_host_free.argtypes = [vp]
+    lib.tg_metrics_csr_dev.argtypes = [vp, vp, i32, vp, i64, i64, vp, vp, vp]
+    lib.tg_bundle_reduce_dev.argtypes = [vp, vp, vp, vp, i64, vp, i64, vp, vp, vp]
+    lib.tg_metrics_csr_host.argtypes = [vp, vp, i32, vp, i64, i64, vp, i64, vp, vp, vp, vp]
+    lib.tg_launch_count.argtypes = [vp, C.POINTER(i64)]
+    for name in EXPORTS:
+        fn = getattr(lib, name)
+        if name not in ("tg_abi_version", "tg_last_error"):
+            fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise TractGeomError(rc, load().tg_last_error().decode(errors="replace"))
+
+
+def _ptr(a):
+    """Host pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Context:
+    """One tg_context: a CUDA device, a stream and grow-only scratch.  Not thread-safe."""
+
+    def __init__(self, device=0):
+        self._h = C.c_void_p()
+        self._lib = load()
+        check(self._lib.tg_create(int(device), C.byref(self._h)))
+        self.device = int(device)
+
+    def close(self):
+        if self._h:
+            self._lib.tg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def synchronize(self):
+        check(self._lib.tg_synchronize(self._h))
+
+    @property
+    def stream(self):
+        s = C.c_void_p()
+        check(self._lib.tg_stream(self._h, C.byref(s)))
+        return s.value or 0
+
+    @property
+    def launches(self):
+        n = C.c_int64()
+        check(self._lib.tg_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # ---- device-pointer calls (ints are raw device addresses, e.g. torch.Tensor.data_ptr()) ----
+    def metrics_dev(self, d_xyz, dtype_code, d_offsets, S, P, d_out, d_keep, stream=0):
+        check(self._lib.tg_metrics_csr_dev(self._h, d_xyz, dtype_code, d_offsets, S, P, d_out, d_keep, stream or None))
+
+    def bundle_reduce_dev(self, d_out, d_keep, d_select, S, bundle_offsets, d_sums, d_counts, stream=0):
+        bo = np.ascontiguousarray(bundle_offsets, dtype=np.int64)
+        check(self._lib.tg_bundle_reduce_dev(self._h, d_out, d_keep, d_select or None, S, _ptr(bo), len(bo) - 1,
+                                             d_sums, d_counts, stream or None))
+
+    # ---- host-buffer call: H2D + kernels + D2H, synchronous ----
+    def metrics_host(self, points, offsets, bundle_offsets=None, want_rows=True):
+        """points (P,3) float64|float32 C-contiguous, offsets int64[S+1].
+
+        Returns (out (17,S) float64 or None, keep uint8[S], sums (B,13), counts (B,14))."""
+        points = np.ascontiguousarray(points)
+        if points.dtype == np.float64:
+            code = F64
+        elif points.dtype == np.float32:
+            code = F32
+        else:
+            points = points.astype(np.float64)
+            code = F64
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        S = len(offsets) - 1
+        P = points.shape[0] if points.ndim == 2 else points.size // 3
+        if bundle_offsets is None:
+            bundle_offsets = np.array([0, S], dtype=np.int64)
+        bo = np.ascontiguousarray(bundle_offsets, dtype=np.int64)
+        B = len(bo) - 1
+        out = np.empty((N_METRICS, S), dtype=np.float64) if want_rows else None
+        keep = np.empty(S, dtype=np.uint8)
+        sums = np.empty((B, N_BUNDLE_COLS), dtype=np.float64)
+        counts = np.empty((B, N_BUNDLE_COLS + 1), dtype=np.int64)
+        check(self._lib.tg_metrics_csr_host(self._h, _ptr(points), code, _ptr(offsets), S, P, _ptr(bo), B,
+                                            _ptr(out), _ptr(keep), _ptr(sums), _ptr(counts)))
+        return out, keep, sums, counts
+
+
+_default_ctx = {}
+
+
+def default_context(device=0):
+    """Process-wide context per device, created lazily and reused (the reference driver calls the
+    hot path 2,368 times per run)."""
+    ctx = _default_ctx.get(device)
+    if ctx is None:
+        ctx = _default_ctx[device] = Context(device)
+    return ctx

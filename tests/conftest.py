@@ -1,0 +1,38 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run on the GPU box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    import numpy as np
+    path = os.path.join(ROOT, "tests", "golden", "golden_v1.npz")
+    z = np.load(path)
+    cases = {}
+    for key in z.files:
+        name, field = key.split("/", 1)
+        cases.setdefault(name, {})[field] = z[key]
+    for name, c in cases.items():
+        if "input_of" in c:
+            src = cases[str(c["input_of"])]
+            c["points"], c["offsets"] = src["points"], src["offsets"]
+        ms = int(c["max_streamlines"])
+        c["max_streamlines"] = None if ms < 0 else ms
+    return cases
+
+
+@pytest.fixture(scope="session")
+def gpu_ctx():
+    """Context on cuda:0.  Fails (does not skip) when the library or device is missing: a GPU test
+    that silently passes without the native code would be worthless."""
+    from lesion_condition_vae_b200 import _lib
+    return _lib.default_context(0)

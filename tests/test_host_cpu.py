@@ -1,0 +1,129 @@
+"""CPU suite, part 2: host-side logic — VTK reader/writer, CSR construction, the drop-in shims,
+and that libtractgeom.so loads and exports every symbol include/tractgeom.h declares."""
+import ctypes
+import gzip
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from lesion_condition_vae_b200 import _lib, synth, vtk_io
+from lesion_condition_vae_b200 import tract_geom_proc as tgp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def small():
+    rng = np.random.default_rng(5)
+    n = np.array([0, 1, 2, 3, 7, 50, 4, 3], dtype=np.int64)
+    return synth.random_walk_csr(n, 5)
+
+
+@pytest.mark.parametrize("binary", [True, False])
+@pytest.mark.parametrize("layout", ["classic", "offsets"])
+@pytest.mark.parametrize("ptype", ["double", "float"])
+def test_vtk_roundtrip(tmp_path, small, binary, layout, ptype):
+    pts, off = small
+    p = vtk_io.write_polylines(tmp_path / "a.vtk", pts, off, binary=binary, point_dtype=ptype, layout=layout)
+    q, o = vtk_io.read_polylines_csr(p)
+    assert np.array_equal(o, off)
+    assert q.dtype == (np.float64 if ptype == "double" else np.float32)
+    assert np.array_equal(q, pts.astype(q.dtype))
+
+
+def test_vtk_gz_and_connectivity(tmp_path, small):
+    pts, off = small
+    perm = np.random.default_rng(1).permutation(len(pts))
+    shuffled = np.empty_like(pts); shuffled[perm] = pts          # point i stored at perm[i]
+    p = vtk_io.write_polylines(tmp_path / "b.vtk.gz", shuffled, off, connectivity=perm)
+    with open(p, "rb") as f:
+        assert f.read(2) == b"\x1f\x8b"
+    q, o = vtk_io.read_polylines_csr(p)
+    assert np.array_equal(o, off) and np.array_equal(q, pts)     # gather by index, ref:19-20
+
+
+def test_vtk_skips_other_sections(tmp_path):
+    txt = (b"# vtk DataFile Version 4.2\nx\nASCII\nDATASET POLYDATA\nPOINTS 4 float\n0 0 0 1 0 0\n1 1 0 2 1 1\n"
+           b"METADATA\nINFORMATION 1\nNAME L2_NORM_RANGE LOCATION vtkDataArray\nDATA 2 0 2.4\n\n"
+           b"VERTICES 1 2\n1 0\nLINES 1 5\n4 0 1 2 3\nPOINT_DATA 4\nSCALARS s float\nLOOKUP_TABLE default\n1 2 3 4\n")
+    p = tmp_path / "c.vtk"; p.write_bytes(txt)
+    q, o = vtk_io.read_polylines_csr(p)
+    assert o.tolist() == [0, 4] and q.shape == (4, 3) and q[3].tolist() == [2, 1, 1]
+
+
+def test_vtk_errors(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        vtk_io.read_polylines_csr(tmp_path / "missing.vtk")
+    p = tmp_path / "bad.vtk"; p.write_bytes(b"hello\n")
+    with pytest.raises(vtk_io.VTKFormatError):
+        vtk_io.read_polylines_csr(p)
+
+
+def test_legacy_lines_walk_matches_reference_loop():
+    lines = np.array([3, 5, 6, 7, 0, 2, 1, 0, 4, 9, 8, 7, 6], dtype=np.int64)
+    off, conn = vtk_io.legacy_lines_to_csr(lines)
+    # the reference's while-loop (tract_geom_proc.py:17-25), restated on the index level
+    i, exp = 0, []
+    while i < len(lines):
+        k = int(lines[i]); exp.append(lines[i + 1:i + 1 + k].tolist()); i += 1 + k
+    got = [conn[off[s]:off[s + 1]].tolist() for s in range(len(off) - 1)]
+    assert got == exp
+    off2, conn2 = vtk_io.legacy_lines_to_csr(np.array([2, 0, 1, 2, 2, 3, 2, 4, 5]), 3)   # uniform fast path
+    assert off2.tolist() == [0, 2, 4, 6] and conn2.tolist() == [0, 1, 2, 3, 4, 5]
+
+
+def test_prefix_rule():
+    n = np.array([5, 2, 9, 0, 3, 3, 1, 4])
+    assert tgp._prefix_for(n, 1) == 1
+    assert tgp._prefix_for(n, 2) == 3
+    assert tgp._prefix_for(n, 4) == 6
+    assert tgp._prefix_for(n, 99) == 8
+    assert tgp._prefix_for(n, 1, start=3) == 5
+
+
+def test_read_streamlines_from_vtk_compat(tmp_path):
+    pts, off = synth.lines_to_csr(synth.adversarial_lines())
+    p = vtk_io.write_polylines(tmp_path / "adv.vtk", pts, off)
+    sls = tgp.read_streamlines_from_vtk(p)
+    assert len(sls) == 11                       # n=2, NaN and inf lines dropped by the loader filter
+    assert len(tgp.read_streamlines_from_vtk(p, max_streamlines=4)) == 4
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    header = open(os.path.join(ROOT, "include", "tractgeom.h")).read()
+    declared = set(re.findall(r"\b(tg_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.tg_abi_version() == 1
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\bT {name}\b", nm), name
+
+
+def test_no_cpu_fallback_without_device():
+    """On a box without a GPU the product path must fail loudly, not compute on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.TractGeomError) as e:
+        _lib.Context(0)
+    assert e.value.code == -4
+    pts, off = synth.config1(S=5)
+    with pytest.raises(_lib.TractGeomError):
+        tgp.compute_streamline_metrics_csr(pts, off)
+
+
+def test_product_code_never_imports_oracle():
+    pkg = os.path.join(ROOT, "lesion_condition_vae_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "reference_runner" not in src and "streamline_oracle" not in src, f
