@@ -1,0 +1,188 @@
+"""GPU suite: the CUDA path, called through the C ABI (include/tractgeom.h via ctypes), against the
+CPU oracle and the reference-generated golden vectors, under the 1e-9 rule of parity_rules.py.
+
+Every test here needs a B200 and libtractgeom.so; a missing library or device FAILS the test."""
+import numpy as np
+import pytest
+
+from lesion_condition_vae_b200 import _lib, synth, vtk_io
+from lesion_condition_vae_b200 import tract_geom_proc as tgp
+from oracle import streamline_oracle as so
+from parity_rules import COLUMNS, assert_bundle_close, assert_table_close
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN_CASES = [
+    "config1", "config1_first100", "adversarial", "adversarial_max1", "adversarial_max3", "adversarial_max5",
+    "adversarial_max6", "adversarial_max8", "ragged_small", "heavy_tail",
+    "config2_t0_tp0", "config2_t3_tp1", "config2_t7_tp2", "config2_t15_tp3", "low_noise",
+]
+
+
+def _oracle_keep(points, offsets):
+    """Expected keep flags, from the oracle's two filters (ref:21 and ref:160)."""
+    S = len(offsets) - 1
+    keep = np.zeros(S, np.uint8)
+    for s in range(S):
+        sl = points[offsets[s]:offsets[s + 1]]
+        if so.loader_accepts(sl):
+            keep[s] |= 1
+            if float(np.linalg.norm(np.diff(sl, axis=0), axis=1).sum()) > so.MIN_LEN:
+                keep[s] |= 2
+    return keep
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_vectors(gpu_ctx, golden, name):
+    c = golden[name]
+    df_sl, df_b = tgp.compute_streamline_metrics_csr(c["points"], c["offsets"], c["max_streamlines"], ctx=gpu_ctx)
+    assert list(df_sl.columns) == list(COLUMNS)
+    assert len(df_sl) == len(c["sl"])                      # streamline count: bit-exact
+    assert df_sl.index.equals(__import__("pandas").RangeIndex(len(df_sl)))
+    assert_table_close(df_sl.to_numpy(), c["sl"], name)
+    assert df_b["n_streamlines"].dtype == np.int64 and int(df_b["n_streamlines"].iloc[0]) == int(c["bundle"][0])
+    assert_bundle_close(df_b.iloc[0].to_numpy(float), c["bundle"], c["sl"], name)
+
+
+@pytest.mark.parametrize("name", ["all_dropped", "empty"])
+def test_empty_result_raises_keyerror_length(gpu_ctx, golden, name):
+    c = golden[name]
+    with pytest.raises(KeyError) as e:
+        tgp.compute_streamline_metrics_csr(c["points"], c["offsets"], c["max_streamlines"], ctx=gpu_ctx)
+    assert e.value.args == ("length",)
+
+
+def test_keep_flags_and_nan_rows(gpu_ctx, golden):
+    c = golden["adversarial"]
+    out, keep, sums, counts = gpu_ctx.metrics_host(c["points"], c["offsets"])
+    exp = _oracle_keep(c["points"], c["offsets"])
+    # the length bit is only defined for loader-accepted rows
+    assert np.array_equal(keep & 1, exp & 1)
+    assert np.array_equal((keep == 3), (exp == 3))
+    assert np.isnan(out[:, keep != 3]).all()
+    assert counts[0, 0] == int((exp == 3).sum())
+
+
+@pytest.mark.parametrize("seed,law", [(21, "uniform"), (22, "normal"), (23, "heavy")])
+def test_random_tracts_vs_oracle(gpu_ctx, seed, law):
+    rng = np.random.default_rng(seed)
+    if law == "uniform":
+        n = synth.lengths_uniform(rng, 600, 3, 160)
+    elif law == "normal":
+        n = synth.lengths_normal(rng, 600)
+    else:
+        n = synth.lengths_heavy_tail(rng, 400, 10, 5000)
+    pts, off = synth.random_walk_csr(n, seed)
+    df_sl, df_b = tgp.compute_streamline_metrics_csr(pts, off, ctx=gpu_ctx)
+    ref_sl, ref_b = so.compute_streamline_metrics_csr(pts, off)
+    assert len(df_sl) == len(ref_sl)
+    assert_table_close(df_sl.to_numpy(), ref_sl.to_numpy(), law)
+    assert_bundle_close(df_b.iloc[0].to_numpy(float), ref_b.iloc[0].to_numpy(float), ref_sl.to_numpy(), law)
+
+
+def test_far_from_origin_covariance(gpu_ctx):
+    """a one-pass raw-coordinate covariance fails at +1000 mm; ours must not."""
+    rng = np.random.default_rng(31)
+    pts, off = synth.random_walk_csr(synth.lengths_uniform(rng, 200, 20, 120), 31)
+    pts = pts + np.array([1000.0, -2000.0, 500.0])
+    df_sl, _ = tgp.compute_streamline_metrics_csr(pts, off, ctx=gpu_ctx)
+    ref_sl, _ = so.compute_streamline_metrics_csr(pts, off)
+    assert_table_close(df_sl.to_numpy(), ref_sl.to_numpy(), "far")
+
+
+def test_float32_points_are_upcast_exactly(gpu_ctx):
+    """float32 storage: the device upcasts exactly, so the result equals the float64 run on the
+    same (float32-representable) values."""
+    pts, off = synth.config1(S=200, seed=8)
+    p32 = pts.astype(np.float32)
+    a = gpu_ctx.metrics_host(p32, off)[0]
+    b = gpu_ctx.metrics_host(p32.astype(np.float64), off)[0]
+    assert np.array_equal(a, b, equal_nan=True)
+    ref_sl, _ = so.compute_streamline_metrics_csr(p32.astype(np.float64), off)
+    assert_table_close(a.T, ref_sl.to_numpy(), "f32")
+
+
+def test_vtk_file_drop_in(gpu_ctx, tmp_path, golden):
+    """The reference-facing call: a path to a legacy VTK file in, two DataFrames out."""
+    c = golden["config1"]
+    for kw in (dict(binary=True, point_dtype="double"), dict(binary=False, point_dtype="double", layout="offsets")):
+        p = vtk_io.write_polylines(tmp_path / "t.vtk", c["points"], c["offsets"], **kw)
+        df_sl, df_b = tgp.compute_streamline_metrics(str(p), max_streamlines=1000)
+        assert_table_close(df_sl.to_numpy(), c["sl"], "vtk")
+        assert_bundle_close(df_b.iloc[0].to_numpy(float), c["bundle"], c["sl"], "vtk")
+    df_sl, df_b = tgp.compute_streamline_metrics(str(p), 100)
+    c = golden["config1_first100"]
+    assert_table_close(df_sl.to_numpy(), c["sl"], "vtk100")
+    with pytest.raises(FileNotFoundError):
+        tgp.compute_streamline_metrics(str(tmp_path / "nope.vtk"))
+
+
+def test_batched_bundles_match_per_bundle_calls(gpu_ctx, golden):
+    """BASELINE config 2 shape: several bundles, one launch; each bundle equals its own golden case."""
+    names = ["config2_t0_tp0", "config2_t3_tp1", "config2_t7_tp2", "config2_t15_tp3"]
+    P, O, B, base = [], [np.zeros(1, np.int64)], [0], 0
+    for nm in names:
+        c = golden[nm]
+        P.append(c["points"]); O.append(c["offsets"][1:] + base); base += int(c["offsets"][-1]); B.append(B[-1] + len(c["offsets"]) - 1)
+    # an empty bundle in the middle and one that drops everything at the end
+    pts = np.concatenate(P + [np.zeros((4, 3))]); off = np.concatenate(O + [np.array([base + 2, base + 4])])
+    # B = [0, s1, s2, s3, s4]; duplicate s2 -> empty bundle #2; trailing bundle of two n=2 polylines
+    bo = np.array(B[:3] + [B[2]] + B[3:] + [B[-1] + 2], dtype=np.int64)
+    res = tgp.compute_bundles_csr(pts, off, bo, ctx=gpu_ctx)
+    assert len(res) == 6
+    got = [res[0], res[1], res[3], res[4]]
+    assert res[2] == (None, None) and res[5] == (None, None)
+    for nm, (df_sl, df_b) in zip(names, got):
+        c = golden[nm]
+        assert_table_close(df_sl.to_numpy(), c["sl"], nm)
+        assert_bundle_close(df_b.iloc[0].to_numpy(float), c["bundle"], c["sl"], nm)
+
+
+def test_device_pointer_abi_and_size_independent_properties(gpu_ctx):
+    """Device-resident call at a size the oracle cannot cover, checked through invariances:
+    rigid translation leaves every metric but the centroid unchanged (to rounding), reversing each
+    polyline preserves length / chord / bbox / centroid / eigen ratios, and a subsample matches the oracle."""
+    import torch
+    dev = torch.device("cuda:0")
+    S = 200_000
+    n = synth.torch_lengths("normal", S, 3, dev)
+    pts, off = synth.torch_random_walk_csr(n, 3, dev)
+    P = pts.shape[0]
+    assert int(off[-1]) == P
+
+    def run(p):
+        out = torch.empty((17, S), dtype=torch.float64, device=dev)
+        keep = torch.empty(S, dtype=torch.uint8, device=dev)
+        gpu_ctx.metrics_dev(p.data_ptr(), _lib.F64, off.data_ptr(), S, P, out.data_ptr(), keep.data_ptr())
+        gpu_ctx.synchronize()
+        return out, keep
+
+    torch.cuda.synchronize()
+    out, keep = run(pts)
+    assert int((keep == 3).sum()) == S                     # count bit-exact: every polyline survives
+    # subsample vs oracle
+    idx = np.unique(np.concatenate([np.arange(300), np.random.default_rng(0).integers(0, S, 300),
+                                    torch.topk(n, 20).indices.cpu().numpy()]))
+    off_h = off.cpu().numpy()
+    rows = []
+    for s in idx:
+        sl = pts[off_h[s]:off_h[s + 1]].cpu().numpy()
+        rows.append(so.metrics_row(sl))
+    assert_table_close(out[:, torch.as_tensor(idx, device=dev)].T.cpu().numpy(), np.asarray(rows), "subsample")
+    # translation
+    shift = torch.tensor([3.0, -7.0, 11.0], dtype=torch.float64, device=dev)
+    out_t, _ = run(pts + shift)
+    same = [m for m in range(17) if m not in (13, 14, 15)]
+    a, b = out[same].cpu().numpy(), out_t[same].cpu().numpy()
+    assert np.all(np.abs(a - b) <= 1e-7 * np.abs(a) + 1e-9)
+    assert torch.allclose(out_t[13:16], out[13:16] + shift[:, None], rtol=0, atol=1e-9)
+    # bundle reduce on device vs torch
+    sums = torch.empty((1, 13), dtype=torch.float64, device=dev)
+    counts = torch.empty((1, 14), dtype=torch.int64, device=dev)
+    gpu_ctx.bundle_reduce_dev(out.data_ptr(), keep.data_ptr(), 0, S, np.array([0, S]), sums.data_ptr(), counts.data_ptr())
+    gpu_ctx.synchronize()
+    src = torch.tensor([0, 2, 4, 6, 7, 8, 10, 11, 12, 16, 13, 14, 15], device=dev)
+    exp = out[src].sum(dim=1)
+    assert torch.allclose(sums[0], exp, rtol=1e-11, atol=0)
+    assert counts[0].tolist() == [S] * 14
+    assert gpu_ctx.launches > 0
