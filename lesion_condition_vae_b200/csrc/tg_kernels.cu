@@ -7,6 +7,7 @@
 // Kernel 2b k_bundle_final    one warp per bundle adds its tiles' partials in tile order, so the
 //                             result does not depend on scheduling.
 #include "tg_device.cuh"
+#include "tg_grouped.cuh"
 #include "tractgeom.h"
 
 #include <cstdio>
@@ -26,11 +27,14 @@ constexpr int kMetricsThreads = 128;
 template <typename T>
 __global__ void __launch_bounds__(kMetricsThreads)
 k_metrics_whole(const T* __restrict__ xyz, const int64_t* __restrict__ offsets, const int64_t S,
-                double* __restrict__ out, uint8_t* __restrict__ keep) {
+                double* __restrict__ out, uint8_t* __restrict__ keep, const int* __restrict__ long_flag, const int64_t min_n) {
+    // long_flag != nullptr: this launch only mops up the polylines k_metrics_grouped left (n > min_n), if any
+    if (long_flag != nullptr && *long_flag == 0) return;
     const int64_t s = (int64_t)blockIdx.x * kMetricsThreads + threadIdx.x;
     if (s >= S) return;
     const int64_t o0 = __ldg(offsets + s), o1 = __ldg(offsets + s + 1);
     const int64_t n64 = o1 - o0;
+    if (n64 <= min_n) return;
     if (n64 < 3) {                                           // ref:21  sl.shape[0] > 2
         const double nan = __longlong_as_double(0x7ff8000000000000LL);
 #pragma unroll
@@ -206,6 +210,9 @@ struct tg_context {
     cudaEvent_t staged = nullptr;     // last H2D out of the pinned staging buffer
     bool staged_pending = false;
     int64_t launches = 0;
+    int sm_count = 148;
+    int* d_flag = nullptr;
+    bool grouped_ready = false;
     // bundle-reduce scratch
     PinBuf h_tiles;                   // TileDesc[nt] followed by int64 tile_first[B+1]
     DevBuf d_tiles, d_tsum, d_tcnt;
@@ -271,6 +278,7 @@ int tg_create(int device, tg_context** out) {
     tg_context* c = new (std::nothrow) tg_context();
     if (!c) return set_err(TG_E_NOMEM, "out of host memory");
     c->device = device;
+    c->sm_count = prop.multiProcessorCount;
     cudaError_t e1 = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     cudaError_t e2 = cudaEventCreateWithFlags(&c->staged, cudaEventDisableTiming);
     if (e1 != cudaSuccess || e2 != cudaSuccess) {
@@ -289,6 +297,7 @@ int tg_destroy(tg_context* c) {
     c->d_tiles.release(); c->d_tsum.release(); c->d_tcnt.release();
     c->d_xyz.release(); c->d_off.release(); c->d_out.release(); c->d_keep.release();
     c->d_sums.release(); c->d_counts.release();
+    if (c->d_flag) cudaFree(c->d_flag);
     cudaEventDestroy(c->staged);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -339,11 +348,24 @@ int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const in
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     const int64_t blocks = (S + tg::kMetricsThreads - 1) / tg::kMetricsThreads;
     if (blocks > 0x7fffffffLL) return set_err(TG_E_INVALID, "too many streamlines for one launch");
-    if (xyz_dtype == TG_F64)
-        tg::k_metrics_whole<double><<<(unsigned)blocks, tg::kMetricsThreads, 0, st>>>((const double*)d_xyz, d_offsets, S, d_out, d_keep);
-    else
-        tg::k_metrics_whole<float><<<(unsigned)blocks, tg::kMetricsThreads, 0, st>>>((const float*)d_xyz, d_offsets, S, d_out, d_keep);
-    c->launches += 1;
+    if (xyz_dtype == TG_F64) {
+        if (((uintptr_t)d_xyz & 7u) != 0) return set_err(TG_E_INVALID, "xyz must be 8-byte aligned");
+        if (!c->d_flag) TG_CUDA(cudaMalloc((void**)&c->d_flag, sizeof(int)));
+        if (!c->grouped_ready) {
+            TG_CUDA(cudaFuncSetAttribute(tg::k_metrics_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::kGroupedSmem));
+            c->grouped_ready = true;
+        }
+        TG_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(int), st));
+        const int64_t tiles = (S + tg::kTile - 1) / tg::kTile;
+        const int64_t ctas = (tiles + tg::kWarpsPerCta - 1) / tg::kWarpsPerCta;
+        const unsigned grid = (unsigned)(ctas < c->sm_count ? ctas : c->sm_count);
+        tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>((const double*)d_xyz, d_offsets, S, d_out, d_keep, c->d_flag);
+        tg::k_metrics_whole<double><<<(unsigned)blocks, tg::kMetricsThreads, 0, st>>>((const double*)d_xyz, d_offsets, S, d_out, d_keep, c->d_flag, (int64_t)tg::kMaxGroupedN);
+        c->launches += 2;
+    } else {
+        tg::k_metrics_whole<float><<<(unsigned)blocks, tg::kMetricsThreads, 0, st>>>((const float*)d_xyz, d_offsets, S, d_out, d_keep, nullptr, (int64_t)-1);
+        c->launches += 1;
+    }
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }
