@@ -17,7 +17,7 @@ SOURCES = ["tg_kernels.cu"]
 HEADERS = ["tg_device.cuh", os.path.join(ROOT, "include", "tractgeom.h")]
 
 NVCC_FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
     "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
     "-I", os.path.join(ROOT, "include"),
 ]

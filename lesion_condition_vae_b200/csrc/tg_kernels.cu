@@ -211,7 +211,7 @@ struct tg_context {
     bool staged_pending = false;
     int64_t launches = 0;
     int sm_count = 148;
-    int* d_flag = nullptr;
+    DevBuf d_qhead, d_hist, d_start, d_perm;   // length-binned queue scratch
     bool grouped_ready = false;
     // bundle-reduce scratch
     PinBuf h_tiles;                   // TileDesc[nt] followed by int64 tile_first[B+1]
@@ -297,7 +297,7 @@ int tg_destroy(tg_context* c) {
     c->d_tiles.release(); c->d_tsum.release(); c->d_tcnt.release();
     c->d_xyz.release(); c->d_off.release(); c->d_out.release(); c->d_keep.release();
     c->d_sums.release(); c->d_counts.release();
-    if (c->d_flag) cudaFree(c->d_flag);
+    c->d_qhead.release(); c->d_hist.release(); c->d_start.release(); c->d_perm.release();
     cudaEventDestroy(c->staged);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -350,18 +350,35 @@ int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const in
     if (blocks > 0x7fffffffLL) return set_err(TG_E_INVALID, "too many streamlines for one launch");
     if (xyz_dtype == TG_F64) {
         if (((uintptr_t)d_xyz & 7u) != 0) return set_err(TG_E_INVALID, "xyz must be 8-byte aligned");
-        if (!c->d_flag) TG_CUDA(cudaMalloc((void**)&c->d_flag, sizeof(int)));
+        if (S > 0x7fffffffLL) return set_err(TG_E_INVALID, "too many streamlines for one launch");
         if (!c->grouped_ready) {
             TG_CUDA(cudaFuncSetAttribute(tg::k_metrics_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::kGroupedSmem));
             c->grouped_ready = true;
         }
-        TG_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(int), st));
-        const int64_t tiles = (S + tg::kTile - 1) / tg::kTile;
-        const int64_t ctas = (tiles + tg::kWarpsPerCta - 1) / tg::kWarpsPerCta;
+        // queue scratch: [flag | total] , hist/cursor, start, perm
+        const int64_t n_windows = (S + tg::kWindow - 1) / tg::kWindow;
+        int rc;
+        if ((rc = c->d_qhead.reserve(64))) return rc;
+        if ((rc = c->d_hist.reserve(sizeof(unsigned) * tg::kBins * (size_t)n_windows))) return rc;
+        if ((rc = c->d_start.reserve(sizeof(int64_t) * tg::kBins * (size_t)n_windows))) return rc;
+        if ((rc = c->d_perm.reserve(sizeof(unsigned) * (size_t)S))) return rc;
+        int* d_flag = (int*)c->d_qhead.p;
+        int64_t* d_total = (int64_t*)((char*)c->d_qhead.p + 8);
+        unsigned* d_hist = (unsigned*)c->d_hist.p;
+        int64_t* d_start = (int64_t*)c->d_start.p;
+        unsigned* d_perm = (unsigned*)c->d_perm.p;
+        TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 64, st));
+        TG_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * tg::kBins * (size_t)n_windows, st));
+        const unsigned seg_grid = (unsigned)((S + tg::kBinSeg - 1) / tg::kBinSeg);
+        tg::k_bin_count<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist);
+        tg::k_bin_scan<<<1, 1024, 0, st>>>(d_hist, n_windows, d_start, d_total);
+        tg::k_bin_scatter<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist, d_start, d_perm, d_out, d_keep, d_flag);
+        const int64_t groups = (S + 31) / 32;
+        const int64_t ctas = (groups + tg::kWarpsPerCta - 1) / tg::kWarpsPerCta;
         const unsigned grid = (unsigned)(ctas < c->sm_count ? ctas : c->sm_count);
-        tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>((const double*)d_xyz, d_offsets, S, d_out, d_keep, c->d_flag);
-        tg::k_metrics_whole<double><<<(unsigned)blocks, tg::kMetricsThreads, 0, st>>>((const double*)d_xyz, d_offsets, S, d_out, d_keep, c->d_flag, (int64_t)tg::kMaxGroupedN);
-        c->launches += 2;
+        tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>((const double*)d_xyz, d_offsets, S, d_perm, d_total, d_out, d_keep);
+        tg::k_metrics_whole<double><<<(unsigned)blocks, tg::kMetricsThreads, 0, st>>>((const double*)d_xyz, d_offsets, S, d_out, d_keep, d_flag, (int64_t)tg::kMaxGroupedN);
+        c->launches += 5;
     } else {
         tg::k_metrics_whole<float><<<(unsigned)blocks, tg::kMetricsThreads, 0, st>>>((const float*)d_xyz, d_offsets, S, d_out, d_keep, nullptr, (int64_t)-1);
         c->launches += 1;
