@@ -144,7 +144,7 @@ __device__ __forceinline__ void sym3_eigenvalues(double a00, double a01, double 
     for (int sweep = 0; sweep < 8; ++sweep) {
         double off = a01 * a01 + a02 * a02 + a12 * a12;
         double dg = a00 * a00 + a11 * a11 + a22 * a22;
-        if (!(off > 1e-40 * dg)) break;
+        if (!(off > 1e-26 * dg)) break;      // |a_pq| < 1e-13 |a|: the eigenvalue error left is ~|a_pq|^2 / gap
         jacobi_rotate(a00, a11, a01, a02, a12);   // (p,q)=(0,1), r=2: arp=a02, arq=a12
         jacobi_rotate(a00, a22, a02, a01, a12);   // (0,2), r=1: arp=a01, arq=a21
         jacobi_rotate(a11, a22, a12, a01, a02);   // (1,2), r=0: arp=a10, arq=a20

@@ -67,8 +67,11 @@ constexpr int kBinSeg = 8192;                 // polylines per CTA of the queue 
 constexpr int kBinThreads = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, int src_bytes) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+// 16-byte cp.async issued iff rem > LIM (one ISETP + one predicated LDGSTS)
+template <int LIM, int OFF>
+__device__ __forceinline__ void cp_async16_if(uint32_t dst, const void* src, int rem) {
+    asm volatile("{ .reg .pred p; setp.gt.s32 p, %2, %3; @p cp.async.cg.shared.global [%0], [%1], 16; }"
+                 ::"r"(dst + OFF), "l"((const unsigned char*)src + OFF), "r"(rem), "n"(LIM) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -153,11 +156,11 @@ k_bin_scan(unsigned* __restrict__ hist, const int64_t n_windows, int64_t* __rest
     if (threadIdx.x == 0) total[0] = run;
 }
 
-// perm[start + rank] = polyline id; polylines with n < 3 get their NaN row (ref:21), longer than
-// kMaxGroupedN raise long_flag.
+// queue[start + rank] = {offset lo, offset hi, n, polyline id}; polylines with n < 3 get their NaN row
+// (ref:21), longer than kMaxGroupedN raise long_flag.
 __global__ void __launch_bounds__(kBinThreads)
 k_bin_scatter(const int64_t* __restrict__ offsets, const int64_t S, unsigned* __restrict__ cursor,
-              const int64_t* __restrict__ start, unsigned* __restrict__ perm, double* __restrict__ out,
+              const int64_t* __restrict__ start, uint4* __restrict__ queue, double* __restrict__ out,
               uint8_t* __restrict__ keep, int* __restrict__ long_flag) {
     __shared__ unsigned sh[kBins];       // pass 1: count; then: next free rank inside this CTA's reservation
     for (int i = threadIdx.x; i < kBins; i += kBinThreads) sh[i] = 0u;
@@ -184,10 +187,11 @@ k_bin_scatter(const int64_t* __restrict__ offsets, const int64_t S, unsigned* __
     }
     __syncthreads();
     for (int64_t s = s0 + threadIdx.x; s < s1; s += kBinThreads) {
-        const int64_t n = __ldg(offsets + s + 1) - __ldg(offsets + s);
+        const int64_t o0 = __ldg(offsets + s);
+        const int64_t n = __ldg(offsets + s + 1) - o0;
         if (n >= 3 && n <= kMaxGroupedN) {
             const unsigned r = atomicAdd(&sh[(int)n], 1u);
-            perm[start[w * kBins + n] + r] = (unsigned)s;
+            queue[start[w * kBins + n] + r] = make_uint4((unsigned)o0, (unsigned)((uint64_t)o0 >> 32), (unsigned)n, (unsigned)s);
         }
     }
 }
@@ -466,38 +470,50 @@ __device__ __forceinline__ unsigned finalize_grouped(const Sums& A, const int n,
 // Kernel 1
 // ==========================================================================================
 __global__ void __launch_bounds__(kGroupedThreads, 1)
-k_metrics_grouped(const double* __restrict__ xyz, const int64_t* __restrict__ offsets, const int64_t S,
-                  const unsigned* __restrict__ perm, const int64_t* __restrict__ queue_len,
+k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const int64_t S,
+                  const uint4* __restrict__ queue, const int64_t* __restrict__ queue_len,
                   double* __restrict__ out, uint8_t* __restrict__ keep) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wsm = smem + warp * kWarpSmem;
     unsigned char* ring = wsm;                                        // 32 x kRingStride
-    uint4* desc = (uint4*)(wsm + 32 * kRingStride);                   // per polyline: {src lo, src hi, total bytes, -}
+    uint4* desc = (uint4*)(wsm + 32 * kRingStride);                   // per polyline: {src lo, src hi, staged bytes, -}
     const uint32_t ring_u32 = smem_u32(ring);
     const unsigned char* my_ring = ring + lane * kRingStride;
+    const uint64_t xyz_end = (uint64_t)(uintptr_t)xyz + 24ull * (uint64_t)P_total;
 
     const int64_t M = *queue_len;
     const int64_t n_groups = (M + 31) >> 5;
     const int64_t warps_total = (int64_t)gridDim.x * kWarpsPerCta;
-    // staging role of this lane: piece (lane & 7) + 8 mm of polyline 4 i + (lane >> 3)
+    // staging role of this lane: pieces (lane & 7) + 8 mm of polylines 4 i + (lane >> 3)
     const int part = lane & 7;
     const uint32_t stage_dst0 = ring_u32 + (lane >> 3) * kRingStride + part * 16;
+    const uint4* stage_desc = desc + (lane >> 3);
 
-    for (int64_t g = (int64_t)blockIdx.x * kWarpsPerCta + warp; g < n_groups; g += warps_total) {
-        const int64_t qi = (g << 5) + lane;
-        const bool act = qi < M;
-        int64_t s = 0, o0 = 0, o1 = 0;
-        if (act) {
-            s = (int64_t)perm[qi];
-            o0 = __ldg(offsets + s); o1 = __ldg(offsets + s + 1);
+    int64_t g = (int64_t)blockIdx.x * kWarpsPerCta + warp;
+    uint4 rec = make_uint4(0u, 0u, 0u, 0u);
+    if (g < n_groups && (g << 5) + lane < M) rec = __ldg(queue + (g << 5) + lane);
+
+    for (; g < n_groups; g += warps_total) {
+        const bool act = (g << 5) + lane < M;
+        const int64_t o0 = (int64_t)(((uint64_t)rec.y << 32) | (uint64_t)rec.x);
+        const int n = act ? (int)rec.z : 0;
+        const int64_t s = (int64_t)rec.w;
+        // prefetch the next group's queue record: its latency hides behind this group's streaming
+        {
+            const int64_t gn = g + warps_total;
+            if (gn < n_groups && (gn << 5) + lane < M) rec = __ldg(queue + (gn << 5) + lane);
         }
-        const int n = act ? (int)(o1 - o0) : 0;
         const double* base = xyz + 3 * o0;
         const uint64_t baddr = (uint64_t)(uintptr_t)base;
         const int skew = act ? (int)(baddr & 15u) : 0;                 // 0 or 8
         const uint64_t a0 = baddr - (uint64_t)skew;
-        const uint32_t total = act ? (uint32_t)(skew + 24 * n) : 0u;   // bytes from a0 to the true end
+        // bytes staged from a0: the polyline rounded up to whole 16-byte pieces — except when that
+        // would read past the end of the point array (only the last polyline can): that one is
+        // left to the exact path, which reads with plain 8-byte loads
+        uint32_t total = act ? (uint32_t)((skew + 24 * n + 15) & ~15) : 0u;
+        bool ok = true;
+        if (act && a0 + total > xyz_end) { ok = false; total -= 16u; }
         desc[lane] = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), total, 0u);
         const int n0 = __shfl_sync(0xffffffffu, n, 0);
         const bool exact = __all_sync(0xffffffffu, act && n == n0) && n0 >= 8;
@@ -508,38 +524,29 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t* __restrict__ of
         const int rounds = (steps + kChunk - 1) / kChunk;
         __syncwarp();
 
-        // shift point for the moments: the middle point (any finite constant works)
-        double m0 = 0.0, m1 = 0.0, m2 = 0.0;
-        if (act) {
-            const double* pm = base + 3 * (int64_t)(n >> 1);
-            m0 = __ldg(pm); m1 = __ldg(pm + 1); m2 = __ldg(pm + 2);
-            if (!(finite_d(m0) && finite_d(m1) && finite_d(m2))) { m0 = m1 = m2 = 0.0; }
-        }
-
-        // cooperative stage of chunk q of all 32 polylines into slot q&1: 8 lanes per polyline,
-        // pieces beyond the end of a polyline are zero-filled without touching memory (src-size 0)
+        // cooperative stage of chunk q of all 32 polylines into slot q&1: 8 lanes per polyline
         auto stage_chunk = [&](const int q) {
             const int pos0 = q * kChunkBytes + part * 16;              // byte position in the aligned stream
             const uint32_t dst0 = stage_dst0 + (q & 1) * kSlotBytes;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const uint4 d = desc[4 * i + (lane >> 3)];
+                const uint4 d = stage_desc[4 * i];
                 const unsigned char* src = (const unsigned char*)(uintptr_t)(((uint64_t)d.y << 32) | (uint64_t)d.x) + pos0;
                 const int rem = (int)d.z - pos0;
                 const uint32_t dst = dst0 + i * (4 * kRingStride);
-                if (rem > 0) cp_async16(dst, src, min(rem, 16));
-                if (rem > 128) cp_async16(dst + 128, src + 128, min(rem - 128, 16));
-                if (part < kPieces - 16 && rem > 256) cp_async16(dst + 256, src + 256, min(rem - 256, 16));
+                cp_async16_if<0, 0>(dst, src, rem);
+                cp_async16_if<128, 128>(dst, src, rem);
+                if (part < kPieces - 16) cp_async16_if<256, 256>(dst, src, rem);
             }
             cp_async_commit();
         };
 
         Sums A;
-        Pipe P;
+        Pipe Q;
         sums_init(A);
-        pipe_init(P);
-        bool ok = true;
+        pipe_init(Q);
         double cx = 0.0, cy = 0.0, cz = 0.0;
+        double m0 = 0.0, m1 = 0.0, m2 = 0.0;                           // shift of the moments: P(0), set at k = 0
         stage_chunk(0);
 #pragma unroll 1
         for (int q = 0; q < rounds; ++q) {
@@ -547,34 +554,52 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t* __restrict__ of
             cp_async_wait<1>();
             __syncwarp();
             const unsigned char* slot = my_ring + (q & 1) * kSlotBytes + skew;
+            if (exact) {
+                // all 32 polylines have n0 points: steps are warp-uniform
 #pragma unroll 1
-            for (int b = 0; b < kChunk / kSub; ++b) {
-                const int k0 = q * kChunk + b * kSub;
-                if (k0 >= steps) break;
-                const double* pp = (const double*)(slot + 24 * kSub * b);
-                // steady <=> every lane is strictly inside its polyline for all kSub steps
-                const bool steady = !act || (k0 >= 4 && k0 + kSub - 1 <= n - 1);
-                if (__all_sync(0xffffffffu, steady)) {
+                for (int b = 0; b < kChunk / kSub; ++b) {
+                    const int k0 = q * kChunk + b * kSub;
+                    const double* pp = (const double*)(slot + 24 * kSub * b);
+                    if (k0 >= 6 && k0 + kSub <= n0) {
 #pragma unroll
-                    for (int i = 0; i < kSub; ++i) {
-                        cx = pp[3 * i]; cy = pp[3 * i + 1]; cz = pp[3 * i + 2];
-                        lane_step<STEADY>(k0 + i, n, cx, cy, cz, m0, m1, m2, P, A, ok);
-                    }
-                } else if (exact) {
+                        for (int i = 0; i < kSub; ++i) {
+                            cx = pp[3 * i]; cy = pp[3 * i + 1]; cz = pp[3 * i + 2];
+                            lane_step<STEADY>(k0 + i, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
+                        }
+                    } else {
 #pragma unroll 1
-                    for (int i = 0; i < kSub; ++i) {
-                        const int k = k0 + i;
-                        if (k > n + 2) break;
-                        if (k < n) { cx = pp[3 * i]; cy = pp[3 * i + 1]; cz = pp[3 * i + 2]; }
-                        lane_step<EDGE>(k, n, cx, cy, cz, m0, m1, m2, P, A, ok);
+                        for (int i = 0; i < kSub; ++i) {
+                            const int k = k0 + i;
+                            if (k > n0 + 2) break;
+                            if (k < n0) { cx = pp[3 * i]; cy = pp[3 * i + 1]; cz = pp[3 * i + 2]; }
+                            if (k == 0) { m0 = cx; m1 = cy; m2 = cz; }
+                            lane_step<EDGE>(k, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
+                        }
                     }
-                } else {
+                }
+            } else {
+#pragma unroll 1
+                for (int b = 0; b < kChunk / kSub; ++b) {
+                    const int k0 = q * kChunk + b * kSub;
+                    if (k0 >= steps) break;
+                    const double* pp = (const double*)(slot + 24 * kSub * b);
+                    // steady <=> every lane is strictly inside its polyline for all kSub steps
+                    const bool steady = !act || (k0 >= 4 && k0 + kSub <= n);
+                    if (__all_sync(0xffffffffu, steady)) {
 #pragma unroll
-                    for (int i = 0; i < kSub; ++i) {
-                        const int k = k0 + i;
-                        const bool ld = act && k < n;
-                        cx = sel(ld, pp[3 * i], cx); cy = sel(ld, pp[3 * i + 1], cy); cz = sel(ld, pp[3 * i + 2], cz);
-                        lane_step<MASKED>(k, n, cx, cy, cz, m0, m1, m2, P, A, ok);
+                        for (int i = 0; i < kSub; ++i) {
+                            cx = pp[3 * i]; cy = pp[3 * i + 1]; cz = pp[3 * i + 2];
+                            lane_step<STEADY>(k0 + i, n, cx, cy, cz, m0, m1, m2, Q, A, ok);
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < kSub; ++i) {
+                            const int k = k0 + i;
+                            const bool ld = act && k < n;
+                            cx = sel(ld, pp[3 * i], cx); cy = sel(ld, pp[3 * i + 1], cy); cz = sel(ld, pp[3 * i + 2], cz);
+                            if (k == 0) { m0 = cx; m1 = cy; m2 = cz; }
+                            lane_step<MASKED>(k, n, cx, cy, cz, m0, m1, m2, Q, A, ok);
+                        }
                     }
                 }
             }
@@ -583,15 +608,10 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t* __restrict__ of
         cp_async_wait<0>();
 
         if (act) {
+            // (m0,m1,m2) = P(0) and (cx,cy,cz) = P(n-1) are still in registers
             const bool fin = finite_d(A.q0) && finite_d(A.q1) && finite_d(A.q2);
-            if (ok && fin) {
-                double f0 = __ldg(base), f1 = __ldg(base + 1), f2 = __ldg(base + 2);
-                const double* pe = base + 3 * (int64_t)(n - 1);
-                double e0 = __ldg(pe), e1 = __ldg(pe + 1), e2 = __ldg(pe + 2);
-                keep[s] = (uint8_t)finalize_grouped(A, n, f0, f1, f2, e0, e1, e2, m0, m1, m2, out, S, s);
-            } else {
-                keep[s] = (uint8_t)slow_polyline(base, n, out, S, s);
-            }
+            if (ok && fin) keep[s] = (uint8_t)finalize_grouped(A, n, m0, m1, m2, cx, cy, cz, m0, m1, m2, out, S, s);
+            else keep[s] = (uint8_t)slow_polyline(base, n, out, S, s);
         }
         __syncwarp();
     }

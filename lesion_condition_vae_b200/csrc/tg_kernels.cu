@@ -361,12 +361,12 @@ int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const in
         if ((rc = c->d_qhead.reserve(64))) return rc;
         if ((rc = c->d_hist.reserve(sizeof(unsigned) * tg::kBins * (size_t)n_windows))) return rc;
         if ((rc = c->d_start.reserve(sizeof(int64_t) * tg::kBins * (size_t)n_windows))) return rc;
-        if ((rc = c->d_perm.reserve(sizeof(unsigned) * (size_t)S))) return rc;
+        if ((rc = c->d_perm.reserve(sizeof(uint4) * (size_t)S))) return rc;
         int* d_flag = (int*)c->d_qhead.p;
         int64_t* d_total = (int64_t*)((char*)c->d_qhead.p + 8);
         unsigned* d_hist = (unsigned*)c->d_hist.p;
         int64_t* d_start = (int64_t*)c->d_start.p;
-        unsigned* d_perm = (unsigned*)c->d_perm.p;
+        uint4* d_perm = (uint4*)c->d_perm.p;
         TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 64, st));
         TG_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * tg::kBins * (size_t)n_windows, st));
         const unsigned seg_grid = (unsigned)((S + tg::kBinSeg - 1) / tg::kBinSeg);
@@ -376,7 +376,7 @@ int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const in
         const int64_t groups = (S + 31) / 32;
         const int64_t ctas = (groups + tg::kWarpsPerCta - 1) / tg::kWarpsPerCta;
         const unsigned grid = (unsigned)(ctas < c->sm_count ? ctas : c->sm_count);
-        tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>((const double*)d_xyz, d_offsets, S, d_perm, d_total, d_out, d_keep);
+        tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>((const double*)d_xyz, P, S, d_perm, d_total, d_out, d_keep);
         tg::k_metrics_whole<double><<<(unsigned)blocks, tg::kMetricsThreads, 0, st>>>((const double*)d_xyz, d_offsets, S, d_out, d_keep, d_flag, (int64_t)tg::kMaxGroupedN);
         c->launches += 5;
     } else {
