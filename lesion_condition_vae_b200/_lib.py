@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtractgeom.so")
+LIB_PATH = os.environ.get("TG_LIB") or os.path.join(HERE, "libtractgeom.so")   # TG_LIB: a tuning variant built by build.py
 
 N_METRICS = 17
 N_BUNDLE_COLS = 13

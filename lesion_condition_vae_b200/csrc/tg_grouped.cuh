@@ -13,8 +13,9 @@
 //   * STAGING.  The points of the 32 polylines of a group go through a per-lane double-buffered
 //     ring in shared memory, filled with cp.async (16-byte pieces, 8 lanes per polyline so every
 //     global request is a whole 128-byte line), kChunk = 12 points per slot, the next slot in
-//     flight while the current one is consumed.  Polylines start on 8-byte boundaries, cp.async
-//     needs 16: a slot carries 16 bytes of lead-out, so a point never straddles two slots.
+//     flight while the current one is consumed.  Polylines start on 8-byte boundaries; the staged
+//     stream starts on the 32-byte sector below (so every request is whole sectors) and a slot
+//     carries one sector of lead-out, so a point never straddles two slots.
 //   * PIPELINE.  Each lane streams its polyline ONCE through a register pipeline
 //         point -> segment/angle -> velocity -> binormal/curvature -> torsion
 //     and keeps the 26 running sums in fp64 registers.
@@ -48,30 +49,42 @@
 
 namespace tg {
 
-constexpr int kWarpsPerCta = 8;
+#ifndef TG_WARPS
+#define TG_WARPS 8
+#endif
+constexpr int kWarpsPerCta = TG_WARPS;
 constexpr int kGroupedThreads = kWarpsPerCta * 32;
 constexpr int kChunk = 12;                    // points per ring slot
 constexpr int kSub = 3;                       // steps per unrolled sub-block (= rotation period of the pipeline registers)
 constexpr int kChunkBytes = kChunk * 24;      // 288
-constexpr int kSlotBytes = kChunkBytes + 16;  // 16-byte lead-out: a point never straddles two slots
-constexpr int kRingStride = 2 * kSlotBytes + 16;   // 624 B per lane: 16-B aligned, 2-way bank conflicts at worst
-constexpr int kPieces = kSlotBytes / 16;      // 19 cp.async pieces per slot
+constexpr int kSlotBytes = kChunkBytes + 32;  // one 32-byte sector of lead-out: a point never straddles two slots
+constexpr int kRingStride = 2 * kSlotBytes + 16;   // 656 B per lane: 16-B aligned, 2-way bank conflicts at worst
+constexpr int kPieces = kSlotBytes / 16;      // 20 cp.async pieces per slot
 constexpr int kWarpSmem = 32 * kRingStride + 32 * 16;   // ring + stream descriptors
 constexpr int kGroupedSmem = kWarpsPerCta * kWarpSmem;
 
 constexpr int kBins = 2048;                   // length bins of the queue
 constexpr int kMaxGroupedN = kBins - 2;       // polylines with more points take the long-polyline kernel
-constexpr int kWindowLog2 = 20;
+#ifndef TG_WINDOW_LOG2
+#define TG_WINDOW_LOG2 17
+#endif
+constexpr int kWindowLog2 = TG_WINDOW_LOG2;
 constexpr int64_t kWindow = (int64_t)1 << kWindowLog2;   // polylines per sorting window
 constexpr int kBinSeg = 8192;                 // polylines per CTA of the queue kernels (divides kWindow)
 constexpr int kBinThreads = 256;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 // 16-byte cp.async issued iff rem > LIM (one ISETP + one predicated LDGSTS)
+// (the points are read exactly once: L2 evict_first keeps them from displacing the output lines)
 template <int LIM, int OFF>
-__device__ __forceinline__ void cp_async16_if(uint32_t dst, const void* src, int rem) {
-    asm volatile("{ .reg .pred p; setp.gt.s32 p, %2, %3; @p cp.async.cg.shared.global [%0], [%1], 16; }"
-                 ::"r"(dst + OFF), "l"((const unsigned char*)src + OFF), "r"(rem), "n"(LIM) : "memory");
+__device__ __forceinline__ void cp_async16_if(uint32_t dst, const void* src, int rem, uint64_t policy) {
+    asm volatile("{ .reg .pred p; setp.gt.s32 p, %2, %3; @p cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %4; }"
+                 ::"r"(dst + OFF), "l"((const unsigned char*)src + OFF), "r"(rem), "n"(LIM), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -471,7 +484,7 @@ __device__ __forceinline__ unsigned finalize_grouped(const Sums& A, const int n,
 // ==========================================================================================
 __global__ void __launch_bounds__(kGroupedThreads, 1)
 k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const int64_t S,
-                  const uint4* __restrict__ queue, const int64_t* __restrict__ queue_len,
+                  const uint4* __restrict__ queue, const int64_t* __restrict__ queue_len, unsigned long long* __restrict__ ticket,
                   double* __restrict__ out, uint8_t* __restrict__ keep) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -481,6 +494,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const i
     const uint32_t ring_u32 = smem_u32(ring);
     const unsigned char* my_ring = ring + lane * kRingStride;
     const uint64_t xyz_end = (uint64_t)(uintptr_t)xyz + 24ull * (uint64_t)P_total;
+    const uint64_t l2_stream = policy_evict_first();
 
     const int64_t M = *queue_len;
     const int64_t n_groups = (M + 31) >> 5;
@@ -490,23 +504,25 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const i
     const uint32_t stage_dst0 = ring_u32 + (lane >> 3) * kRingStride + part * 16;
     const uint4* stage_desc = desc + (lane >> 3);
 
+    // dynamic group queue: the first round of groups is static, later ones come from a global ticket
     int64_t g = (int64_t)blockIdx.x * kWarpsPerCta + warp;
     uint4 rec = make_uint4(0u, 0u, 0u, 0u);
     if (g < n_groups && (g << 5) + lane < M) rec = __ldg(queue + (g << 5) + lane);
 
-    for (; g < n_groups; g += warps_total) {
+    while (g < n_groups) {
         const bool act = (g << 5) + lane < M;
         const int64_t o0 = (int64_t)(((uint64_t)rec.y << 32) | (uint64_t)rec.x);
         const int n = act ? (int)rec.z : 0;
         const int64_t s = (int64_t)rec.w;
-        // prefetch the next group's queue record: its latency hides behind this group's streaming
-        {
-            const int64_t gn = g + warps_total;
-            if (gn < n_groups && (gn << 5) + lane < M) rec = __ldg(queue + (gn << 5) + lane);
-        }
+        // take the next ticket and prefetch that group's queue record: the latency of both hides
+        // behind this group's streaming
+        int64_t gn = 0;
+        if (lane == 0) gn = warps_total + (int64_t)atomicAdd(ticket, 1ull);
+        gn = __shfl_sync(0xffffffffu, gn, 0);
+        if (gn < n_groups && (gn << 5) + lane < M) rec = __ldg(queue + (gn << 5) + lane);
         const double* base = xyz + 3 * o0;
         const uint64_t baddr = (uint64_t)(uintptr_t)base;
-        const int skew = act ? (int)(baddr & 15u) : 0;                 // 0 or 8
+        const int skew = act ? (int)(baddr & 31u) : 0;                 // 0, 8, 16 or 24
         const uint64_t a0 = baddr - (uint64_t)skew;
         // bytes staged from a0: the polyline rounded up to whole 16-byte pieces — except when that
         // would read past the end of the point array (only the last polyline can): that one is
@@ -514,6 +530,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const i
         uint32_t total = act ? (uint32_t)((skew + 24 * n + 15) & ~15) : 0u;
         bool ok = true;
         if (act && a0 + total > xyz_end) { ok = false; total -= 16u; }
+        if (act && a0 < (uint64_t)(uintptr_t)xyz) { ok = false; total = 0u; }   // would read below the array (unaligned xyz): exact path
         desc[lane] = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), total, 0u);
         const int n0 = __shfl_sync(0xffffffffu, n, 0);
         const bool exact = __all_sync(0xffffffffu, act && n == n0) && n0 >= 8;
@@ -534,9 +551,9 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const i
                 const unsigned char* src = (const unsigned char*)(uintptr_t)(((uint64_t)d.y << 32) | (uint64_t)d.x) + pos0;
                 const int rem = (int)d.z - pos0;
                 const uint32_t dst = dst0 + i * (4 * kRingStride);
-                cp_async16_if<0, 0>(dst, src, rem);
-                cp_async16_if<128, 128>(dst, src, rem);
-                if (part < kPieces - 16) cp_async16_if<256, 256>(dst, src, rem);
+                cp_async16_if<0, 0>(dst, src, rem, l2_stream);
+                cp_async16_if<128, 128>(dst, src, rem, l2_stream);
+                if (part < kPieces - 16) cp_async16_if<256, 256>(dst, src, rem, l2_stream);
             }
             cp_async_commit();
         };
@@ -548,36 +565,62 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const i
         double cx = 0.0, cy = 0.0, cz = 0.0;
         double m0 = 0.0, m1 = 0.0, m2 = 0.0;                           // shift of the moments: P(0), set at k = 0
         stage_chunk(0);
+        if (exact) {
+            // ---- all 32 polylines have n0 >= 8 points: every step is warp-uniform.
+            //      head k = 0..5 and tail k = n0..n0+2 are compile-time specialisations of the EDGE step
+            //      (every predicate folds), the interior runs the predicate-free STEADY step.
+            __builtin_assume(n0 >= 8);
+            const int rounds_e = (n0 + kChunk - 1) / kChunk;           // rounds that bring in points
 #pragma unroll 1
-        for (int q = 0; q < rounds; ++q) {
-            if (q + 1 < rounds) stage_chunk(q + 1); else cp_async_commit();
-            cp_async_wait<1>();
-            __syncwarp();
-            const unsigned char* slot = my_ring + (q & 1) * kSlotBytes + skew;
-            if (exact) {
-                // all 32 polylines have n0 points: steps are warp-uniform
+            for (int q = 0; q < rounds_e; ++q) {
+                if (q + 1 < rounds_e) stage_chunk(q + 1); else cp_async_commit();
+                cp_async_wait<1>();
+                __syncwarp();
+                const unsigned char* slot = my_ring + (q & 1) * kSlotBytes + skew;
+                int b = 0;
+                if (q == 0) {
+                    const double* pp = (const double*)slot;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        cx = pp[3 * k]; cy = pp[3 * k + 1]; cz = pp[3 * k + 2];
+                        if (k == 0) { m0 = cx; m1 = cy; m2 = cz; }
+                        lane_step<EDGE>(k, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
+                    }
+                    b = 2;
+                }
 #pragma unroll 1
-                for (int b = 0; b < kChunk / kSub; ++b) {
+                for (; b < kChunk / kSub; ++b) {
                     const int k0 = q * kChunk + b * kSub;
                     const double* pp = (const double*)(slot + 24 * kSub * b);
-                    if (k0 >= 6 && k0 + kSub <= n0) {
+                    if (k0 + kSub <= n0) {
 #pragma unroll
                         for (int i = 0; i < kSub; ++i) {
                             cx = pp[3 * i]; cy = pp[3 * i + 1]; cz = pp[3 * i + 2];
                             lane_step<STEADY>(k0 + i, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
                         }
                     } else {
+                        // the last 0..2 interior points
 #pragma unroll 1
-                        for (int i = 0; i < kSub; ++i) {
-                            const int k = k0 + i;
-                            if (k > n0 + 2) break;
-                            if (k < n0) { cx = pp[3 * i]; cy = pp[3 * i + 1]; cz = pp[3 * i + 2]; }
-                            if (k == 0) { m0 = cx; m1 = cy; m2 = cz; }
-                            lane_step<EDGE>(k, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
+                        for (int k = k0; k < n0; ++k) {
+                            cx = pp[3 * (k - k0)]; cy = pp[3 * (k - k0) + 1]; cz = pp[3 * (k - k0) + 2];
+                            lane_step<STEADY>(k, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
                         }
+                        break;
                     }
                 }
-            } else {
+                __syncwarp();
+            }
+            // drain: (cx,cy,cz) = P(n0-1) held
+            lane_step<EDGE>(n0, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
+            lane_step<EDGE>(n0 + 1, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
+            lane_step<EDGE>(n0 + 2, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
+        } else {
+#pragma unroll 1
+            for (int q = 0; q < rounds; ++q) {
+                if (q + 1 < rounds) stage_chunk(q + 1); else cp_async_commit();
+                cp_async_wait<1>();
+                __syncwarp();
+                const unsigned char* slot = my_ring + (q & 1) * kSlotBytes + skew;
 #pragma unroll 1
                 for (int b = 0; b < kChunk / kSub; ++b) {
                     const int k0 = q * kChunk + b * kSub;
@@ -602,8 +645,8 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const i
                         }
                     }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         }
         cp_async_wait<0>();
 
@@ -614,6 +657,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const i
             else keep[s] = (uint8_t)slow_polyline(base, n, out, S, s);
         }
         __syncwarp();
+        g = gn;
     }
 }
 

@@ -376,7 +376,7 @@ int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const in
         const int64_t groups = (S + 31) / 32;
         const int64_t ctas = (groups + tg::kWarpsPerCta - 1) / tg::kWarpsPerCta;
         const unsigned grid = (unsigned)(ctas < c->sm_count ? ctas : c->sm_count);
-        tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>((const double*)d_xyz, P, S, d_perm, d_total, d_out, d_keep);
+        tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>((const double*)d_xyz, P, S, d_perm, d_total, (unsigned long long*)((char*)c->d_qhead.p + 16), d_out, d_keep);
         tg::k_metrics_whole<double><<<(unsigned)blocks, tg::kMetricsThreads, 0, st>>>((const double*)d_xyz, d_offsets, S, d_out, d_keep, d_flag, (int64_t)tg::kMaxGroupedN);
         c->launches += 5;
     } else {
