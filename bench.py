@@ -186,7 +186,7 @@ def run_reference(args):
 def run_ours(args):
     import numpy as np
     import torch
-    from lesion_condition_vae_b200 import _lib, synth
+    from lesion_condition_vae_b200 import _lib, sharding, synth
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -210,10 +210,9 @@ def run_ours(args):
     del n
     out = torch.empty((17, S), dtype=torch.float64, device=dev)
     keep = torch.empty(S, dtype=torch.uint8, device=dev)
-    part = torch.zeros(27, dtype=torch.float64, device=dev)      # 13 sums | 14 counts (as f64) -> all-gather payload
+    part = torch.zeros((1, sharding.PARTIAL_WIDTH), dtype=torch.float64, device=dev)   # 13 sums | 14 counts (as f64): all-gather payload
     sums = torch.empty((1, 13), dtype=torch.float64, device=dev)
     counts = torch.empty((1, 14), dtype=torch.int64, device=dev)
-    gathered = torch.empty((world, 27), dtype=torch.float64, device=dev) if world > 1 else None
     bo = np.array([0, S], dtype=np.int64)
     stream = torch.cuda.Stream(dev)           # a real (non-default) stream: kernels AND timing events live on it
     torch.cuda.set_stream(stream)
@@ -228,10 +227,9 @@ def run_ours(args):
             ev[1].record(stream)
         ctx.bundle_reduce_dev(out.data_ptr(), keep.data_ptr(), 0, S, bo, sums.data_ptr(), counts.data_ptr(), sp)
         if world > 1:
-            part[:13] = sums[0]
-            part[13:] = counts[0].to(torch.float64)              # exact: counts < 2^53
-            dist.all_gather_into_tensor(gathered, part)
-            return gathered.sum(dim=0)                           # rank-ordered partials -> identical on all ranks
+            part[0, :13] = sums[0]
+            part[0, 13:] = counts[0].to(torch.float64)           # exact: counts < 2^53
+            return sharding.allgather_partials(part)             # (world, 1, 27): summed in rank order by the caller
         return None
 
     for _ in range(max(args.warmup, 3)):
@@ -272,9 +270,13 @@ def run_ours(args):
     sec = ms_total / 1e3
     value = tot_S * args.steps / sec
 
-    # sanity: the result is real (every polyline kept, finite lengths)
-    n_kept = int(counts[0, 0].item())
-    mean_len = float(sums[0, 0].item()) / max(n_kept, 1)
+    # sanity: the result is real (every polyline kept, finite lengths); at N > 1 from the gathered partials
+    if world > 1:
+        g_sums, g_counts = sharding.combine_partials(step().cpu().numpy())
+        n_kept = int(g_counts[0, 0]); mean_len = float(g_sums[0, 0]) / max(int(g_counts[0, 1]), 1)
+    else:
+        n_kept = int(counts[0, 0].item())
+        mean_len = float(sums[0, 0].item()) / max(n_kept, 1)
 
     # ---- e2e: HOST buffers through tg_metrics_csr_host (pinned), H2D + kernels + D2H per step ----
     Se = min(args.e2e_streamlines, S)

@@ -62,6 +62,21 @@ k_metrics_whole(const T* __restrict__ xyz, const int64_t* __restrict__ offsets, 
     keep[s] = (uint8_t)finalize_metrics(A, n, f0, f1, f2, e0, e1, e2, m0, m1, m2, out, S, s);
 }
 
+// float32 storage: exact upcast into a float64 scratch copy, then the float64 path (so a float32
+// file gives bit-identical results to the same values stored as float64)
+__global__ void __launch_bounds__(256)
+k_upcast_f32(const float* __restrict__ src, double* __restrict__ dst, const int64_t count) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < count; i += stride) {
+        if (i + 3 < count && (((uintptr_t)(src + i)) & 15u) == 0) {
+            const float4 v = *reinterpret_cast<const float4*>(src + i);
+            dst[i] = (double)v.x; dst[i + 1] = (double)v.y; dst[i + 2] = (double)v.z; dst[i + 3] = (double)v.w;
+        } else {
+            for (int64_t j = i; j < count && j < i + 4; ++j) dst[j] = (double)src[j];
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // Kernel 2: bundle partial moments
 // ------------------------------------------------------------------------------------------
@@ -212,6 +227,7 @@ struct tg_context {
     int64_t launches = 0;
     int sm_count = 148;
     DevBuf d_qhead, d_hist, d_start, d_perm;   // length-binned queue scratch
+    DevBuf d_xyz64;                            // float64 copy of float32 input
     bool grouped_ready = false;
     // bundle-reduce scratch
     PinBuf h_tiles;                   // TileDesc[nt] followed by int64 tile_first[B+1]
@@ -297,7 +313,7 @@ int tg_destroy(tg_context* c) {
     c->d_tiles.release(); c->d_tsum.release(); c->d_tcnt.release();
     c->d_xyz.release(); c->d_off.release(); c->d_out.release(); c->d_keep.release();
     c->d_sums.release(); c->d_counts.release();
-    c->d_qhead.release(); c->d_hist.release(); c->d_start.release(); c->d_perm.release();
+    c->d_xyz64.release(); c->d_qhead.release(); c->d_hist.release(); c->d_start.release(); c->d_perm.release();
     cudaEventDestroy(c->staged);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -348,7 +364,19 @@ int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const in
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     const int64_t blocks = (S + tg::kMetricsThreads - 1) / tg::kMetricsThreads;
     if (blocks > 0x7fffffffLL) return set_err(TG_E_INVALID, "too many streamlines for one launch");
-    if (xyz_dtype == TG_F64) {
+    if (xyz_dtype == TG_F32) {
+        int rc0;
+        if ((rc0 = c->d_xyz64.reserve(sizeof(double) * 3 * (size_t)P + 64))) return rc0;
+        if (P > 0) {
+            const int64_t count = 3 * P;
+            const int64_t want = (count / 4 + 255) / 256;
+            const unsigned g = (unsigned)(want < (int64_t)c->sm_count * 16 ? (want > 0 ? want : 1) : (int64_t)c->sm_count * 16);
+            tg::k_upcast_f32<<<g, 256, 0, st>>>((const float*)d_xyz, (double*)c->d_xyz64.p, count);
+            c->launches += 1;
+        }
+        d_xyz = c->d_xyz64.p;
+    }
+    {
         if (((uintptr_t)d_xyz & 7u) != 0) return set_err(TG_E_INVALID, "xyz must be 8-byte aligned");
         if (S > 0x7fffffffLL) return set_err(TG_E_INVALID, "too many streamlines for one launch");
         if (!c->grouped_ready) {
@@ -379,9 +407,6 @@ int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const in
         tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>((const double*)d_xyz, P, S, d_perm, d_total, (unsigned long long*)((char*)c->d_qhead.p + 16), d_out, d_keep);
         tg::k_metrics_whole<double><<<(unsigned)blocks, tg::kMetricsThreads, 0, st>>>((const double*)d_xyz, d_offsets, S, d_out, d_keep, d_flag, (int64_t)tg::kMaxGroupedN);
         c->launches += 5;
-    } else {
-        tg::k_metrics_whole<float><<<(unsigned)blocks, tg::kMetricsThreads, 0, st>>>((const float*)d_xyz, d_offsets, S, d_out, d_keep, nullptr, (int64_t)-1);
-        c->launches += 1;
     }
     TG_CUDA(cudaGetLastError());
     return TG_OK;

@@ -1,0 +1,87 @@
+"""Multi-GPU plumbing of the streamline-metrics path: CSR range sharding and the bundle-partial
+exchange.
+
+Polylines are independent (every stencil stays inside one polyline), so the tractogram shards by
+contiguous CSR ranges, balanced by POINT count, with no data-path collective.  The only
+cross-polyline step of the reference is the 13-column nan-mean per bundle
+(/root/reference/src/geometry/tract_geom_proc.py:191-210): every rank reduces its own shard to
+``B x 27`` partial moments (13 sums, the kept-row count, 13 non-NaN counts), ONE all-gather moves
+them (216 bytes per bundle per rank: latency-bound on NVLink/NVSwitch), and every rank adds the
+gathered partials in rank order — deterministic and identical on all ranks, which an all-reduce
+would not guarantee.
+
+``torch.distributed`` is plumbing only: NCCL for device tensors, gloo for the CPU tests.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+N_BUNDLE_COLS = 13
+PARTIAL_WIDTH = 2 * N_BUNDLE_COLS + 1          # 13 sums | n_streamlines | 13 non-NaN counts
+
+
+def shard_ranges(offsets, world_size):
+    """Split polylines [0, S) into ``world_size`` contiguous ranges holding ~P/world_size points each.
+
+    Returns int64[world_size + 1] polyline boundaries (non-decreasing, first 0, last S)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    S = len(offsets) - 1
+    P = int(offsets[-1]) - int(offsets[0])
+    targets = int(offsets[0]) + (np.arange(1, world_size, dtype=np.float64) * P / world_size)
+    cuts = np.searchsorted(offsets, targets, side="left").astype(np.int64)
+    cuts = np.clip(cuts, 0, S)
+    bounds = np.concatenate([[0], cuts, [S]]).astype(np.int64)
+    return np.maximum.accumulate(bounds)
+
+
+def shard_csr(points, offsets, lo, hi):
+    """The CSR slice of polylines [lo, hi): (points view, rebased offsets copy)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    p0, p1 = int(offsets[lo]), int(offsets[hi])
+    return points[p0:p1], offsets[lo:hi + 1] - p0
+
+
+def shard_bundle_offsets(bundle_offsets, lo, hi):
+    """Bundle table of the shard [lo, hi): every bundle keeps its index, clipped to the shard
+    (bundles outside it become empty), rebased to the shard's first polyline."""
+    bo = np.asarray(bundle_offsets, dtype=np.int64)
+    return np.clip(bo, lo, hi) - lo
+
+
+def pack_partials(sums, counts):
+    """(B,13) float64 sums + (B,14) int64 counts -> (B,27) float64 (counts < 2^53 are exact)."""
+    sums = np.asarray(sums, dtype=np.float64).reshape(-1, N_BUNDLE_COLS)
+    counts = np.asarray(counts, dtype=np.int64).reshape(-1, N_BUNDLE_COLS + 1)
+    return np.concatenate([sums, counts.astype(np.float64)], axis=1)
+
+
+def combine_partials(gathered):
+    """(world, B, 27) gathered partials -> (sums (B,13), counts (B,14)), added in rank order."""
+    g = np.asarray(gathered, dtype=np.float64)
+    total = np.zeros(g.shape[1:], dtype=np.float64)
+    for r in range(g.shape[0]):                      # fixed order: same result on every rank
+        total = total + g[r]
+    sums = total[:, :N_BUNDLE_COLS]
+    counts = np.rint(total[:, N_BUNDLE_COLS:]).astype(np.int64)
+    return sums, counts
+
+
+def means_from_partials(sums, counts):
+    """n_streamlines (B,) and the 13 nan-means (B,13): sum / non-NaN count, NaN where the count is 0."""
+    with np.errstate(invalid="ignore", divide="ignore"):
+        means = np.where(counts[:, 1:] > 0, sums / np.maximum(counts[:, 1:], 1), np.nan)
+    return counts[:, 0].copy(), means
+
+
+def allgather_partials(partial, group=None):
+    """All-gather a (B,27) float64 torch tensor (CPU with gloo, CUDA with NCCL) -> (world, B, 27)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    flat = partial.contiguous().view(-1)
+    out = torch.empty(world * flat.numel(), dtype=partial.dtype, device=partial.device)
+    if partial.is_cuda:
+        dist.all_gather_into_tensor(out, flat, group=group)
+    else:                                            # gloo has no flat all-gather: gather into views
+        dist.all_gather(list(out.view(world, -1).unbind(0)), flat, group=group)
+    return out.view((world,) + tuple(partial.shape))
