@@ -121,9 +121,10 @@ class Context:
                                              d_sums, d_counts, stream or None))
 
     # ---- host-buffer call: H2D + kernels + D2H, synchronous ----
-    def metrics_host(self, points, offsets, bundle_offsets=None, want_rows=True):
+    def metrics_host(self, points, offsets, bundle_offsets=None, want_rows=True, out=None, keep=None):
         """points (P,3) float64|float32 C-contiguous, offsets int64[S+1].
 
+        ``out`` / ``keep``: optional preallocated result arrays (e.g. pinned memory).
         Returns (out (17,S) float64 or None, keep uint8[S], sums (B,13), counts (B,14))."""
         points = np.ascontiguousarray(points)
         if points.dtype == np.float64:
@@ -140,8 +141,12 @@ class Context:
             bundle_offsets = np.array([0, S], dtype=np.int64)
         bo = np.ascontiguousarray(bundle_offsets, dtype=np.int64)
         B = len(bo) - 1
-        out = np.empty((N_METRICS, S), dtype=np.float64) if want_rows else None
-        keep = np.empty(S, dtype=np.uint8)
+        if out is None:
+            out = np.empty((N_METRICS, S), dtype=np.float64) if want_rows else None
+        if keep is None:
+            keep = np.empty(S, dtype=np.uint8)
+        assert out is None or (out.shape == (N_METRICS, S) and out.dtype == np.float64)
+        assert keep.shape == (S,) and keep.dtype == np.uint8
         sums = np.empty((B, N_BUNDLE_COLS), dtype=np.float64)
         counts = np.empty((B, N_BUNDLE_COLS + 1), dtype=np.int64)
         check(self._lib.tg_metrics_csr_host(self._h, _ptr(points), code, _ptr(offsets), S, P, _ptr(bo), B,

@@ -170,11 +170,12 @@ k_bin_scan(unsigned* __restrict__ hist, const int64_t n_windows, int64_t* __rest
 }
 
 // queue[start + rank] = {offset lo, offset hi, n, polyline id}; polylines with n < 3 get their NaN row
-// (ref:21), longer than kMaxGroupedN raise long_flag.
+// (ref:21); ids of polylines longer than kMaxGroupedN are appended, downwards, at the END of the
+// queue buffer (records + ids never exceed its S x 16 bytes) and counted in n_long.
 __global__ void __launch_bounds__(kBinThreads)
 k_bin_scatter(const int64_t* __restrict__ offsets, const int64_t S, unsigned* __restrict__ cursor,
               const int64_t* __restrict__ start, uint4* __restrict__ queue, double* __restrict__ out,
-              uint8_t* __restrict__ keep, int* __restrict__ long_flag) {
+              const int64_t ld, uint8_t* __restrict__ keep, int* __restrict__ n_long) {
     __shared__ unsigned sh[kBins];       // pass 1: count; then: next free rank inside this CTA's reservation
     for (int i = threadIdx.x; i < kBins; i += kBinThreads) sh[i] = 0u;
     __syncthreads();
@@ -182,17 +183,16 @@ k_bin_scatter(const int64_t* __restrict__ offsets, const int64_t S, unsigned* __
     const int64_t s1 = min(s0 + kBinSeg, S);
     const int64_t w = s0 >> kWindowLog2;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    bool any_long = false;
+    unsigned* long_end = (unsigned*)(queue + S);
     for (int64_t s = s0 + threadIdx.x; s < s1; s += kBinThreads) {
         const int64_t n = __ldg(offsets + s + 1) - __ldg(offsets + s);
         if (n >= 3 && n <= kMaxGroupedN) atomicAdd(&sh[(int)n], 1u);
         else if (n < 3) {
 #pragma unroll
-            for (int m = 0; m < 17; ++m) out[(int64_t)m * S + s] = nan;
+            for (int m = 0; m < 17; ++m) out[(int64_t)m * ld + s] = nan;
             keep[s] = 0;
-        } else any_long = true;
+        } else long_end[-1 - (int64_t)atomicAdd(n_long, 1)] = (unsigned)s;
     }
-    if (any_long) atomicOr(long_flag, 1);
     __syncthreads();
     for (int i = threadIdx.x; i < kBins; i += kBinThreads) {
         const unsigned c = sh[i];
@@ -483,7 +483,9 @@ __device__ __forceinline__ unsigned finalize_grouped(const Sums& A, const int n,
 // Kernel 1
 // ==========================================================================================
 __global__ void __launch_bounds__(kGroupedThreads, 1)
-k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const int64_t S,
+// xyz may be a VIRTUAL base (chunked host path): [xyz_lo, xyz_hi) is the byte range that may be read;
+// ld = column stride of `out` (polylines of the whole table).
+k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const uint64_t xyz_hi, const int64_t ld,
                   const uint4* __restrict__ queue, const int64_t* __restrict__ queue_len, unsigned long long* __restrict__ ticket,
                   double* __restrict__ out, uint8_t* __restrict__ keep) {
     extern __shared__ __align__(128) unsigned char smem[];
@@ -493,7 +495,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const i
     uint4* desc = (uint4*)(wsm + 32 * kRingStride);                   // per polyline: {src lo, src hi, staged bytes, -}
     const uint32_t ring_u32 = smem_u32(ring);
     const unsigned char* my_ring = ring + lane * kRingStride;
-    const uint64_t xyz_end = (uint64_t)(uintptr_t)xyz + 24ull * (uint64_t)P_total;
+    const uint64_t xyz_end = xyz_hi;
     const uint64_t l2_stream = policy_evict_first();
 
     const int64_t M = *queue_len;
@@ -530,7 +532,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const i
         uint32_t total = act ? (uint32_t)((skew + 24 * n + 15) & ~15) : 0u;
         bool ok = true;
         if (act && a0 + total > xyz_end) { ok = false; total -= 16u; }
-        if (act && a0 < (uint64_t)(uintptr_t)xyz) { ok = false; total = 0u; }   // would read below the array (unaligned xyz): exact path
+        if (act && a0 < xyz_lo) { ok = false; total = 0u; }   // would read below the array (unaligned xyz): exact path
         desc[lane] = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), total, 0u);
         const int n0 = __shfl_sync(0xffffffffu, n, 0);
         const bool exact = __all_sync(0xffffffffu, act && n == n0) && n0 >= 8;
@@ -653,8 +655,8 @@ k_metrics_grouped(const double* __restrict__ xyz, const int64_t P_total, const i
         if (act) {
             // (m0,m1,m2) = P(0) and (cx,cy,cz) = P(n-1) are still in registers
             const bool fin = finite_d(A.q0) && finite_d(A.q1) && finite_d(A.q2);
-            if (ok && fin) keep[s] = (uint8_t)finalize_grouped(A, n, m0, m1, m2, cx, cy, cz, m0, m1, m2, out, S, s);
-            else keep[s] = (uint8_t)slow_polyline(base, n, out, S, s);
+            if (ok && fin) keep[s] = (uint8_t)finalize_grouped(A, n, m0, m1, m2, cx, cy, cz, m0, m1, m2, out, ld, s);
+            else keep[s] = (uint8_t)slow_polyline(base, n, out, ld, s);
         }
         __syncwarp();
         g = gn;

@@ -1,7 +1,8 @@
 // tg_kernels.cu — kernels + C ABI (include/tractgeom.h) of the streamline-metrics path, sm_100a.
 //
-// Kernel 1  k_metrics_whole   one lane walks one polyline through the register pipeline of
-//                             tg_device.cuh and writes its 17 metrics + keep flags.
+// Kernel 1  (tg_grouped.cuh)  k_bin_count / k_bin_scan / k_bin_scatter: length-binned work queue;
+//                             k_metrics_grouped: one polyline per lane, 17 metrics + keep flags.
+//            k_metrics_long   polylines too long for the queue bins: one warp per polyline.
 // Kernel 2a k_bundle_tiles    per-tile partial moments of the 13 aggregated columns (tiles never
 //                             straddle a bundle boundary) — ref:191-210 of tract_geom_proc.py.
 // Kernel 2b k_bundle_final    one warp per bundle adds its tiles' partials in tile order, so the
@@ -16,50 +17,68 @@
 #include <new>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 namespace tg {
 
 // ------------------------------------------------------------------------------------------
-// Kernel 1
+// Long polylines (more than kMaxGroupedN points): one WARP per polyline.  Every lane streams one
+// contiguous chunk through the exact general pipeline of tg_device.cuh (with its 3-point halo),
+// the 32 partial sums are merged pairwise in index order (Chan's formula for the curvature
+// moments) and lane 0 finalises.  Rare by construction; keeps heavy-tailed tractograms balanced.
 // ------------------------------------------------------------------------------------------
-constexpr int kMetricsThreads = 128;
+constexpr int kLongThreads = 128;
 
-template <typename T>
-__global__ void __launch_bounds__(kMetricsThreads)
-k_metrics_whole(const T* __restrict__ xyz, const int64_t* __restrict__ offsets, const int64_t S,
-                double* __restrict__ out, uint8_t* __restrict__ keep, const int* __restrict__ long_flag, const int64_t min_n) {
-    // long_flag != nullptr: this launch only mops up the polylines k_metrics_grouped left (n > min_n), if any
-    if (long_flag != nullptr && *long_flag == 0) return;
-    const int64_t s = (int64_t)blockIdx.x * kMetricsThreads + threadIdx.x;
-    if (s >= S) return;
-    const int64_t o0 = __ldg(offsets + s), o1 = __ldg(offsets + s + 1);
-    const int64_t n64 = o1 - o0;
-    if (n64 <= min_n) return;
-    if (n64 < 3) {                                           // ref:21  sl.shape[0] > 2
-        const double nan = __longlong_as_double(0x7ff8000000000000LL);
-#pragma unroll
-        for (int m = 0; m < TG_N_METRICS; ++m) out[(int64_t)m * S + s] = nan;
-        keep[s] = 0;
-        return;
+__device__ __forceinline__ double shfl_down_d(double v, int o) { return __shfl_down_sync(0xffffffffu, v, o); }
+__device__ __forceinline__ void acc_shfl_down(const Acc& A, Acc& B, int o) {
+    B.L = shfl_down_d(A.L, o); B.th = shfl_down_d(A.th, o);
+    B.w0 = shfl_down_d(A.w0, o); B.w1 = shfl_down_d(A.w1, o); B.w2 = shfl_down_d(A.w2, o); B.ww = shfl_down_d(A.ww, o);
+    B.q0 = shfl_down_d(A.q0, o); B.q1 = shfl_down_d(A.q1, o); B.q2 = shfl_down_d(A.q2, o);
+    B.q00 = shfl_down_d(A.q00, o); B.q01 = shfl_down_d(A.q01, o); B.q02 = shfl_down_d(A.q02, o);
+    B.q11 = shfl_down_d(A.q11, o); B.q12 = shfl_down_d(A.q12, o); B.q22 = shfl_down_d(A.q22, o);
+    B.mn0 = shfl_down_d(A.mn0, o); B.mn1 = shfl_down_d(A.mn1, o); B.mn2 = shfl_down_d(A.mn2, o);
+    B.mx0 = shfl_down_d(A.mx0, o); B.mx1 = shfl_down_d(A.mx1, o); B.mx2 = shfl_down_d(A.mx2, o);
+    B.kK = shfl_down_d(A.kK, o); B.k1 = shfl_down_d(A.k1, o); B.k2 = shfl_down_d(A.k2, o);
+    B.en = shfl_down_d(A.en, o); B.ta = shfl_down_d(A.ta, o);
+    B.kn = __shfl_down_sync(0xffffffffu, A.kn, o); B.tn = __shfl_down_sync(0xffffffffu, A.tn, o);
+    B.absmax_hi = __shfl_down_sync(0xffffffffu, A.absmax_hi, o);
+}
+
+__global__ void __launch_bounds__(kLongThreads)
+k_metrics_long(const double* __restrict__ xyz, const int64_t* __restrict__ offsets, const int64_t ld,
+               const unsigned* __restrict__ long_list_end, const int* __restrict__ n_long,
+               double* __restrict__ out, uint8_t* __restrict__ keep) {
+    const int count = *n_long;
+    const int lane = threadIdx.x & 31;
+    const int warps_total = gridDim.x * (kLongThreads / 32);
+    for (int idx = blockIdx.x * (kLongThreads / 32) + (threadIdx.x >> 5); idx < count; idx += warps_total) {
+        const int64_t s = (int64_t)long_list_end[-1 - (int64_t)idx];           // ids are stored downwards from the end of the queue buffer
+        const int64_t o0 = __ldg(offsets + s), o1 = __ldg(offsets + s + 1);
+        const int n = (int)min(o1 - o0, (int64_t)0x7ffffff0);
+        const double* base = xyz + 3 * o0;
+        double f0, f1, f2, g0, g1, g2, m0, m1, m2, e0, e1, e2;
+        load_point(base, f0, f1, f2);
+        load_point(base + 3, g0, g1, g2);
+        load_point(base + 3 * (int64_t)(n >> 1), m0, m1, m2);
+        load_point(base + 3 * (int64_t)(n - 1), e0, e1, e2);
+        double rx = g0 - f0, ry = g1 - f1, rz = g2 - f2, rl, ri;
+        norm_and_inv_eps(rx * rx + ry * ry + rz * rz, rl, ri);
+        rx *= ri; ry *= ri; rz *= ri;
+        if (!(finite_d(rx) && finite_d(ry) && finite_d(rz))) { rx = ry = rz = 0.0; }
+        if (!(finite_d(m0) && finite_d(m1) && finite_d(m2))) { m0 = m1 = m2 = 0.0; }
+        const int cs = (n + 31) / 32;
+        const int c0 = min(lane * cs, n), c1 = min(c0 + cs, n);
+        Acc A, B;
+        acc_init(A);
+        if (c0 < c1) stream_chunk<double, false>(base, n, c0, c1, rx, ry, rz, m0, m1, m2, A);
+#pragma unroll 1
+        for (int o = 1; o < 32; o <<= 1) {
+            acc_shfl_down(A, B, o);
+            if ((lane & (2 * o - 1)) == 0) acc_merge(A, B);
+        }
+        if (lane == 0) keep[s] = (uint8_t)finalize_metrics(A, n, f0, f1, f2, e0, e1, e2, m0, m1, m2, out, ld, s);
+        __syncwarp();
     }
-    const int n = (int)n64;
-    const T* base = xyz + 3 * o0;
-    double f0, f1, f2, g0, g1, g2, m0, m1, m2, e0, e1, e2;
-    load_point(base, f0, f1, f2);
-    load_point(base + 3, g0, g1, g2);
-    load_point(base + 3 * (int64_t)(n >> 1), m0, m1, m2);
-    load_point(base + 3 * (int64_t)(n - 1), e0, e1, e2);
-    // reference direction r ~ first unit segment: any constant works (the dispersion is shift
-    // invariant); this one makes the shifted sums small for nearly straight polylines.
-    double rx = g0 - f0, ry = g1 - f1, rz = g2 - f2, rl, ri;
-    norm_and_inv_eps(rx * rx + ry * ry + rz * rz, rl, ri);
-    rx *= ri; ry *= ri; rz *= ri;
-    if (!(finite_d(rx) && finite_d(ry) && finite_d(rz))) { rx = ry = rz = 0.0; }
-    if (!(finite_d(m0) && finite_d(m1) && finite_d(m2))) { m0 = m1 = m2 = 0.0; }
-    Acc A;
-    acc_init(A);
-    stream_chunk<T, true>(base, n, 0, n, rx, ry, rz, m0, m1, m2, A);
-    keep[s] = (uint8_t)finalize_metrics(A, n, f0, f1, f2, e0, e1, e2, m0, m1, m2, out, S, s);
 }
 
 // float32 storage: exact upcast into a float64 scratch copy, then the float64 path (so a float32
@@ -228,6 +247,8 @@ struct tg_context {
     int sm_count = 148;
     DevBuf d_qhead, d_hist, d_start, d_perm;   // length-binned queue scratch
     DevBuf d_xyz64;                            // float64 copy of float32 input
+    cudaStream_t s_copy = nullptr, s_back = nullptr;   // H2D / D2H streams of the chunked host path
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr};
     bool grouped_ready = false;
     // bundle-reduce scratch
     PinBuf h_tiles;                   // TileDesc[nt] followed by int64 tile_first[B+1]
@@ -314,6 +335,7 @@ int tg_destroy(tg_context* c) {
     c->d_xyz.release(); c->d_off.release(); c->d_out.release(); c->d_keep.release();
     c->d_sums.release(); c->d_counts.release();
     c->d_xyz64.release(); c->d_qhead.release(); c->d_hist.release(); c->d_start.release(); c->d_perm.release();
+    if (c->s_copy) { cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_back); for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_h2d[i]); cudaEventDestroy(c->ev_comp[i]); } }
     cudaEventDestroy(c->staged);
     cudaStreamDestroy(c->stream);
     delete c;
@@ -353,6 +375,57 @@ int tg_launch_count(tg_context* c, int64_t* launches) {
     return TG_OK;
 }
 
+// Queue + streaming + long-polyline kernels for S polylines whose points are float64.
+//   xyz      base such that polyline s starts at xyz + 3*offsets[s] (may be virtual: chunked host path)
+//   lo, hi   byte range of the point array that may be read
+//   ld       column stride of d_out (>= S); d_out / d_keep already point at this range's first polyline
+static int launch_metrics_f64(tg_context* c, const double* xyz, uint64_t lo, uint64_t hi, const int64_t* d_offsets, int64_t S,
+                              double* d_out, int64_t ld, uint8_t* d_keep, cudaStream_t st) {
+    if (S > 0x7fffffffLL) return set_err(TG_E_INVALID, "too many streamlines for one launch");
+    if (!c->grouped_ready) {
+        TG_CUDA(cudaFuncSetAttribute(tg::k_metrics_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::kGroupedSmem));
+        c->grouped_ready = true;
+    }
+    // queue scratch: [n_long | total | ticket], hist/cursor, start, queue records (+ long ids at the end)
+    const int64_t n_windows = (S + tg::kWindow - 1) / tg::kWindow;
+    int rc;
+    if ((rc = c->d_qhead.reserve(64))) return rc;
+    if ((rc = c->d_hist.reserve(sizeof(unsigned) * tg::kBins * (size_t)n_windows))) return rc;
+    if ((rc = c->d_start.reserve(sizeof(int64_t) * tg::kBins * (size_t)n_windows))) return rc;
+    if ((rc = c->d_perm.reserve(sizeof(uint4) * (size_t)S))) return rc;
+    int* d_nlong = (int*)c->d_qhead.p;
+    int64_t* d_total = (int64_t*)((char*)c->d_qhead.p + 8);
+    unsigned long long* d_ticket = (unsigned long long*)((char*)c->d_qhead.p + 16);
+    unsigned* d_hist = (unsigned*)c->d_hist.p;
+    int64_t* d_start = (int64_t*)c->d_start.p;
+    uint4* d_queue = (uint4*)c->d_perm.p;
+    TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 64, st));
+    TG_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * tg::kBins * (size_t)n_windows, st));
+    const unsigned seg_grid = (unsigned)((S + tg::kBinSeg - 1) / tg::kBinSeg);
+    tg::k_bin_count<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist);
+    tg::k_bin_scan<<<1, 1024, 0, st>>>(d_hist, n_windows, d_start, d_total);
+    tg::k_bin_scatter<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist, d_start, d_queue, d_out, ld, d_keep, d_nlong);
+    const int64_t groups = (S + 31) / 32;
+    const int64_t ctas = (groups + tg::kWarpsPerCta - 1) / tg::kWarpsPerCta;
+    const unsigned grid = (unsigned)(ctas < c->sm_count ? ctas : c->sm_count);
+    tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>(xyz, lo, hi, ld, d_queue, d_total, d_ticket, d_out, d_keep);
+    tg::k_metrics_long<<<(unsigned)c->sm_count * 4u, tg::kLongThreads, 0, st>>>(xyz, d_offsets, ld, (const unsigned*)(d_queue + S), d_nlong, d_out, d_keep);
+    c->launches += 5;
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+static int upcast_f32(tg_context* c, const void* d_src, int64_t count, double* d_dst, cudaStream_t st) {
+    if (count <= 0) return TG_OK;
+    const int64_t want = (count / 4 + 255) / 256;
+    const int64_t cap = (int64_t)c->sm_count * 16;
+    const unsigned g = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+    tg::k_upcast_f32<<<g, 256, 0, st>>>((const float*)d_src, d_dst, count);
+    c->launches += 1;
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
 int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const int64_t* d_offsets, int64_t S, int64_t P,
                        double* d_out, uint8_t* d_keep, void* stream) {
     if (!c) return set_err(TG_E_INVALID, "null context");
@@ -362,54 +435,15 @@ int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const in
     if (!d_offsets || !d_out || !d_keep || (P > 0 && !d_xyz)) return set_err(TG_E_INVALID, "null device pointer");
     DeviceGuard g(c->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
-    const int64_t blocks = (S + tg::kMetricsThreads - 1) / tg::kMetricsThreads;
-    if (blocks > 0x7fffffffLL) return set_err(TG_E_INVALID, "too many streamlines for one launch");
+    int rc;
     if (xyz_dtype == TG_F32) {
-        int rc0;
-        if ((rc0 = c->d_xyz64.reserve(sizeof(double) * 3 * (size_t)P + 64))) return rc0;
-        if (P > 0) {
-            const int64_t count = 3 * P;
-            const int64_t want = (count / 4 + 255) / 256;
-            const unsigned g = (unsigned)(want < (int64_t)c->sm_count * 16 ? (want > 0 ? want : 1) : (int64_t)c->sm_count * 16);
-            tg::k_upcast_f32<<<g, 256, 0, st>>>((const float*)d_xyz, (double*)c->d_xyz64.p, count);
-            c->launches += 1;
-        }
+        if ((rc = c->d_xyz64.reserve(sizeof(double) * 3 * (size_t)P + 64))) return rc;
+        if ((rc = upcast_f32(c, d_xyz, 3 * P, (double*)c->d_xyz64.p, st))) return rc;
         d_xyz = c->d_xyz64.p;
     }
-    {
-        if (((uintptr_t)d_xyz & 7u) != 0) return set_err(TG_E_INVALID, "xyz must be 8-byte aligned");
-        if (S > 0x7fffffffLL) return set_err(TG_E_INVALID, "too many streamlines for one launch");
-        if (!c->grouped_ready) {
-            TG_CUDA(cudaFuncSetAttribute(tg::k_metrics_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::kGroupedSmem));
-            c->grouped_ready = true;
-        }
-        // queue scratch: [flag | total] , hist/cursor, start, perm
-        const int64_t n_windows = (S + tg::kWindow - 1) / tg::kWindow;
-        int rc;
-        if ((rc = c->d_qhead.reserve(64))) return rc;
-        if ((rc = c->d_hist.reserve(sizeof(unsigned) * tg::kBins * (size_t)n_windows))) return rc;
-        if ((rc = c->d_start.reserve(sizeof(int64_t) * tg::kBins * (size_t)n_windows))) return rc;
-        if ((rc = c->d_perm.reserve(sizeof(uint4) * (size_t)S))) return rc;
-        int* d_flag = (int*)c->d_qhead.p;
-        int64_t* d_total = (int64_t*)((char*)c->d_qhead.p + 8);
-        unsigned* d_hist = (unsigned*)c->d_hist.p;
-        int64_t* d_start = (int64_t*)c->d_start.p;
-        uint4* d_perm = (uint4*)c->d_perm.p;
-        TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 64, st));
-        TG_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * tg::kBins * (size_t)n_windows, st));
-        const unsigned seg_grid = (unsigned)((S + tg::kBinSeg - 1) / tg::kBinSeg);
-        tg::k_bin_count<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist);
-        tg::k_bin_scan<<<1, 1024, 0, st>>>(d_hist, n_windows, d_start, d_total);
-        tg::k_bin_scatter<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist, d_start, d_perm, d_out, d_keep, d_flag);
-        const int64_t groups = (S + 31) / 32;
-        const int64_t ctas = (groups + tg::kWarpsPerCta - 1) / tg::kWarpsPerCta;
-        const unsigned grid = (unsigned)(ctas < c->sm_count ? ctas : c->sm_count);
-        tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>((const double*)d_xyz, P, S, d_perm, d_total, (unsigned long long*)((char*)c->d_qhead.p + 16), d_out, d_keep);
-        tg::k_metrics_whole<double><<<(unsigned)blocks, tg::kMetricsThreads, 0, st>>>((const double*)d_xyz, d_offsets, S, d_out, d_keep, d_flag, (int64_t)tg::kMaxGroupedN);
-        c->launches += 5;
-    }
-    TG_CUDA(cudaGetLastError());
-    return TG_OK;
+    if (((uintptr_t)d_xyz & 7u) != 0) return set_err(TG_E_INVALID, "xyz must be 8-byte aligned");
+    const uint64_t lo = (uint64_t)(uintptr_t)d_xyz;
+    return launch_metrics_f64(c, (const double*)d_xyz, lo, lo + 24ull * (uint64_t)P, d_offsets, S, d_out, S, d_keep, st);
 }
 
 int tg_bundle_reduce_dev(tg_context* c, const double* d_out, const uint8_t* d_keep, const uint8_t* d_select, int64_t S,
@@ -480,25 +514,79 @@ int tg_metrics_csr_host(tg_context* c, const void* h_xyz, int xyz_dtype, const i
     DeviceGuard g(c->device);
     const size_t esz = xyz_dtype == TG_F64 ? 8 : 4;
     int rc;
-    if ((rc = c->d_xyz.reserve(esz * 3 * (size_t)P))) return rc;
+    // ---- chunk plan: contiguous polyline ranges of at most ~chunk_points points each, so that the
+    //      H2D copy of chunk i+1, the kernels of chunk i and the D2H of chunk i-1 overlap
+    int64_t chunk_points = 8ll << 20;
+    if (const char* e = getenv("TG_HOST_CHUNK_POINTS")) { long long v = atoll(e); if (v > 0) chunk_points = v; }
+    std::vector<int64_t> cuts;
+    cuts.push_back(0);
+    int64_t max_pts = 0;
+    while (cuts.back() < S) {
+        const int64_t s0 = cuts.back();
+        const int64_t* it = std::upper_bound(h_off + s0 + 1, h_off + S + 1, h_off[s0] + chunk_points);
+        int64_t s1 = (int64_t)(it - h_off) - 1;
+        if (s1 <= s0) s1 = s0 + 1;
+        cuts.push_back(s1);
+        max_pts = std::max(max_pts, h_off[s1] - h_off[s0]);
+    }
+    const int n_chunks = (int)cuts.size() - 1;
+    // chunk buffers carry 256 bytes of slack on both sides: the staging of k_metrics_grouped may then read
+    // whole sectors around the first / last polyline of a chunk, so no polyline is pushed to the exact path
+    // just because of where the chunk boundary fell (results do not depend on the chunking)
+    const size_t buf_stride = ((esz * 3 * (size_t)max_pts + 255) & ~(size_t)255) + 512;
+    if ((rc = c->d_xyz.reserve(2 * buf_stride))) return rc;
+    if (xyz_dtype == TG_F32 && (rc = c->d_xyz64.reserve(sizeof(double) * 3 * (size_t)max_pts + 512))) return rc;
     if ((rc = c->d_off.reserve(sizeof(int64_t) * (size_t)(S + 1)))) return rc;
     if ((rc = c->d_out.reserve(sizeof(double) * TG_N_METRICS * (size_t)S))) return rc;
     if ((rc = c->d_keep.reserve((size_t)S))) return rc;
     if ((rc = c->d_sums.reserve(sizeof(double) * tg::kNB * (size_t)B))) return rc;
     if ((rc = c->d_counts.reserve(sizeof(int64_t) * (tg::kNB + 1) * (size_t)B))) return rc;
+    if (!c->s_copy) {
+        TG_CUDA(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+        TG_CUDA(cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            TG_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+            TG_CUDA(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+        }
+    }
     cudaStream_t st = c->stream;
-    if (P > 0) TG_CUDA(cudaMemcpyAsync(c->d_xyz.p, h_xyz, esz * 3 * (size_t)P, cudaMemcpyHostToDevice, st));
+    double* d_out = (double*)c->d_out.p;
+    uint8_t* d_keep = (uint8_t*)c->d_keep.p;
+    const int64_t* d_off = (const int64_t*)c->d_off.p;
     TG_CUDA(cudaMemcpyAsync(c->d_off.p, h_off, sizeof(int64_t) * (size_t)(S + 1), cudaMemcpyHostToDevice, st));
-    if ((rc = tg_metrics_csr_dev(c, c->d_xyz.p, xyz_dtype, (const int64_t*)c->d_off.p, S, P, (double*)c->d_out.p, (uint8_t*)c->d_keep.p, st))) return rc;
+    for (int i = 0; i < n_chunks; ++i) {
+        const int b = i & 1;
+        const int64_t s0 = cuts[i], s1 = cuts[i + 1], p0 = h_off[s0], np = h_off[s1] - p0;
+        char* d_buf = (char*)c->d_xyz.p + (size_t)b * buf_stride + 256;
+        if (i >= 2) TG_CUDA(cudaStreamWaitEvent(c->s_copy, c->ev_comp[b], 0));       // buffer b is free again
+        if (np > 0) TG_CUDA(cudaMemcpyAsync(d_buf, (const char*)h_xyz + esz * 3 * (size_t)p0, esz * 3 * (size_t)np, cudaMemcpyHostToDevice, c->s_copy));
+        TG_CUDA(cudaEventRecord(c->ev_h2d[b], c->s_copy));
+        TG_CUDA(cudaStreamWaitEvent(st, c->ev_h2d[b], 0));
+        const double* d_pts = (const double*)d_buf;
+        if (xyz_dtype == TG_F32) {
+            if ((rc = upcast_f32(c, d_buf, 3 * np, (double*)((char*)c->d_xyz64.p + 256), st))) return rc;
+            d_pts = (const double*)((char*)c->d_xyz64.p + 256);
+        }
+        const uint64_t lo = (uint64_t)(uintptr_t)d_pts;
+        const double* xyz_virtual = (const double*)(uintptr_t)(lo - 24ull * (uint64_t)p0);   // polyline s starts at xyz_virtual + 3*offsets[s]
+        if ((rc = launch_metrics_f64(c, xyz_virtual, lo - 32, lo + 24ull * (uint64_t)np + 32, d_off + s0, s1 - s0, d_out + s0, S, d_keep + s0, st))) return rc;
+        TG_CUDA(cudaEventRecord(c->ev_comp[b], st));
+        if (h_out || h_keep) {
+            TG_CUDA(cudaStreamWaitEvent(c->s_back, c->ev_comp[b], 0));
+            if (h_out)
+                for (int m = 0; m < TG_N_METRICS; ++m)
+                    TG_CUDA(cudaMemcpyAsync(h_out + (size_t)m * S + s0, d_out + (size_t)m * S + s0, sizeof(double) * (size_t)(s1 - s0), cudaMemcpyDeviceToHost, c->s_back));
+            if (h_keep) TG_CUDA(cudaMemcpyAsync(h_keep + s0, d_keep + s0, (size_t)(s1 - s0), cudaMemcpyDeviceToHost, c->s_back));
+        }
+    }
     if (B > 0) {
-        if ((rc = tg_bundle_reduce_dev(c, (const double*)c->d_out.p, (const uint8_t*)c->d_keep.p, nullptr, S, h_bo, B,
-                                       (double*)c->d_sums.p, (int64_t*)c->d_counts.p, st))) return rc;
+        if ((rc = tg_bundle_reduce_dev(c, d_out, d_keep, nullptr, S, h_bo, B, (double*)c->d_sums.p, (int64_t*)c->d_counts.p, st))) return rc;
         TG_CUDA(cudaMemcpyAsync(h_sums, c->d_sums.p, sizeof(double) * tg::kNB * (size_t)B, cudaMemcpyDeviceToHost, st));
         TG_CUDA(cudaMemcpyAsync(h_counts, c->d_counts.p, sizeof(int64_t) * (tg::kNB + 1) * (size_t)B, cudaMemcpyDeviceToHost, st));
     }
-    if (h_out && S > 0) TG_CUDA(cudaMemcpyAsync(h_out, c->d_out.p, sizeof(double) * TG_N_METRICS * (size_t)S, cudaMemcpyDeviceToHost, st));
-    if (h_keep && S > 0) TG_CUDA(cudaMemcpyAsync(h_keep, c->d_keep.p, (size_t)S, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(c->s_copy));
     TG_CUDA(cudaStreamSynchronize(st));
+    TG_CUDA(cudaStreamSynchronize(c->s_back));
     return TG_OK;
 }
 

@@ -186,3 +186,24 @@ def test_device_pointer_abi_and_size_independent_properties(gpu_ctx):
     assert torch.allclose(sums[0], exp, rtol=1e-11, atol=0)
     assert counts[0].tolist() == [S] * 14
     assert gpu_ctx.launches > 0
+
+
+def test_chunked_host_pipeline_equals_single_shot(gpu_ctx, monkeypatch):
+    """tg_metrics_csr_host streams the tractogram in polyline-aligned chunks (H2D / kernels / D2H
+    overlapped); the table must be bit-identical whatever the chunk size, for float64 and float32."""
+    rng = np.random.default_rng(41)
+    n = np.concatenate([synth.lengths_uniform(rng, 700, 0, 90), [2500, 3, 2047, 2046, 4100]])
+    pts, off = synth.random_walk_csr(n, 41)
+    bo = np.array([0, 100, 100, 650, len(n)], dtype=np.int64)
+    for arr in (pts, pts.astype(np.float32)):
+        monkeypatch.delenv("TG_HOST_CHUNK_POINTS", raising=False)
+        a = gpu_ctx.metrics_host(arr, off, bo)
+        for cp in ("1", "777", "20000"):
+            monkeypatch.setenv("TG_HOST_CHUNK_POINTS", cp)
+            b = gpu_ctx.metrics_host(arr, off, bo)
+            assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1])
+            assert np.array_equal(a[3], b[3]) and np.allclose(a[2], b[2], rtol=1e-13, atol=0)
+    monkeypatch.delenv("TG_HOST_CHUNK_POINTS", raising=False)
+    ref_sl, _ = so.compute_streamline_metrics_csr(pts, off)
+    out, keep, _, _ = gpu_ctx.metrics_host(pts, off)
+    assert_table_close(out[:, keep == 3].T, ref_sl.to_numpy(), "chunked+long")
