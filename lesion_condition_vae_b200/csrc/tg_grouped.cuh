@@ -54,8 +54,16 @@ namespace tg {
 #endif
 constexpr int kWarpsPerCta = TG_WARPS;
 constexpr int kGroupedThreads = kWarpsPerCta * 32;
-constexpr int kChunk = 12;                    // points per ring slot
-constexpr int kSub = 3;                       // steps per unrolled sub-block (= rotation period of the pipeline registers)
+#ifndef TG_CHUNK
+#define TG_CHUNK 12
+#endif
+#ifndef TG_SUB
+#define TG_SUB 3
+#endif
+constexpr int kChunk = TG_CHUNK;              // points per ring slot (even, multiple of kSub)
+constexpr int kSub = TG_SUB;                  // steps per unrolled sub-block (3 = rotation period of the pipeline registers)
+constexpr int kHead = ((6 + kSub - 1) / kSub) * kSub;   // first steps of a polyline, run as specialised EDGE steps (>= 4 needed)
+static_assert(kChunk % kSub == 0 && kChunk % 2 == 0 && kHead <= kChunk, "chunk / sub-block geometry");
 constexpr int kChunkBytes = kChunk * 24;      // 288
 constexpr int kSlotBytes = kChunkBytes + 32;  // one 32-byte sector of lead-out: a point never straddles two slots
 constexpr int kRingStride = 2 * kSlotBytes + 16;   // 656 B per lane: 16-B aligned, 2-way bank conflicts at worst
@@ -216,7 +224,14 @@ struct Sums {
     double L, th;                  // sum |d_j|, sum theta_i
     double t0, t1, t2, su;         // sum t_j, sum (1 - |t_j|^2)/2
     double q0, q1, q2, q00, q01, q02, q11, q12, q22;   // moments of p - m
+#ifndef TG_BBOX_INT
+#define TG_BBOX_INT 0
+#endif
+#if TG_BBOX_INT
+    long long mn0, mn1, mn2, mx0, mx1, mx2;   // bounding box as order-preserving integer keys (integer pipe, not fp64)
+#else
     double mn0, mn1, mn2, mx0, mx1, mx2;
+#endif
     double kK, k1, k2, en, ta;     // curvature shift / shifted moments, energy, torsion sum
 };
 struct Pipe {
@@ -229,10 +244,22 @@ struct Pipe {
 __device__ __forceinline__ void sums_init(Sums& A) {
     A.L = A.th = A.t0 = A.t1 = A.t2 = A.su = 0.0;
     A.q0 = A.q1 = A.q2 = A.q00 = A.q01 = A.q02 = A.q11 = A.q12 = A.q22 = 0.0;
+#if TG_BBOX_INT
+    A.mn0 = A.mn1 = A.mn2 = 0x7fffffffffffffffLL;
+    A.mx0 = A.mx1 = A.mx2 = (long long)0x8000000000000000ULL;
+#else
     A.mn0 = A.mn1 = A.mn2 = __longlong_as_double(0x7ff0000000000000LL);
     A.mx0 = A.mx1 = A.mx2 = __longlong_as_double(0xfff0000000000000LL);
+#endif
     A.kK = A.k1 = A.k2 = A.en = A.ta = 0.0;
 }
+// double <-> signed 64-bit key with the same ordering (an involution: flip the low 63 bits of negatives)
+__device__ __forceinline__ long long order_key(double x) {
+    const long long b = __double_as_longlong(x);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double key_value(long long k) { return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL)); }
+__device__ __forceinline__ double key_value(double k) { return k; }
 __device__ __forceinline__ void pipe_init(Pipe& S) {
     S.p1x = S.p1y = S.p1z = S.p2x = S.p2y = S.p2z = 0.0;
     S.tx = S.ty = S.tz = S.u_prev = S.len_prev = 0.0;
@@ -316,9 +343,14 @@ __device__ __forceinline__ void lane_step(const int k, const int n, const double
         A.q00 = fma(qx, qx, A.q00); A.q01 = fma(qx, qy, A.q01); A.q02 = fma(qx, qz, A.q02);
         A.q11 = fma(qy, qy, A.q11); A.q12 = fma(qy, qz, A.q12); A.q22 = fma(qz, qz, A.q22);
         const bool mp = MODE != MASKED || pP;
-        A.mn0 = sel(mp && cx < A.mn0, cx, A.mn0); A.mx0 = sel(mp && cx > A.mx0, cx, A.mx0);
-        A.mn1 = sel(mp && cy < A.mn1, cy, A.mn1); A.mx1 = sel(mp && cy > A.mx1, cy, A.mx1);
-        A.mn2 = sel(mp && cz < A.mn2, cz, A.mn2); A.mx2 = sel(mp && cz > A.mx2, cz, A.mx2);
+#if TG_BBOX_INT
+        const long long kx = order_key(cx), ky = order_key(cy), kz = order_key(cz);
+#else
+        const double kx = cx, ky = cy, kz = cz;
+#endif
+        A.mn0 = (mp && kx < A.mn0) ? kx : A.mn0; A.mx0 = (mp && kx > A.mx0) ? kx : A.mx0;
+        A.mn1 = (mp && ky < A.mn1) ? ky : A.mn1; A.mx1 = (mp && ky > A.mx1) ? ky : A.mx1;
+        A.mn2 = (mp && kz < A.mn2) ? kz : A.mn2; A.mx2 = (mp && kz > A.mx2) ? kz : A.mx2;
     }
 
     // ---- segment stage j = k-1 (ref:32-33, 102, 145) and bending angle i = k-2 (ref:98-106)
@@ -374,18 +406,19 @@ __device__ __forceinline__ void lane_step(const int k, const int n, const double
         ok = ok && (!pB || kok);
         if (MODE != STEADY && k == 2) A.kK = kappa;                        // shift for the moments: kappa_0
         double dk = kappa - A.kK;
-        double ek = (kappa * kappa) * (S.len_prev + kEps);                 // ref:77,82-83
+        double kk = kappa * kappa;                                         // ref:77,82-83: kappa^2 (|d_j| + eps)
+        double ds = S.len_prev + kEps;
         if (MODE == MASKED) {
             dk = sel(pB, dk, 0.0);
-            ek = sel(pE, ek, 0.0);
+            kk = sel(pE, kk, 0.0); ds = sel(pE, ds, 0.0);                  // 0*0: a masked-off lane may hold NaN in either
             bnx = sel(pB, x, bnx); bny = sel(pB, y, bny); bnz = sel(pB, z, bnz); bbn = sel(pB, bb, bbn);
         } else {
-            if (MODE == EDGE && !pE) ek = 0.0;
+            if (MODE == EDGE && !pE) kk = 0.0;
             bnx = x; bny = y; bnz = z; bbn = bb;
         }
         A.k1 += dk;
         A.k2 = fma(dk, dk, A.k2);
-        A.en += ek;
+        A.en = fma(kk, ds, A.en);
     }
 
     // ---- torsion stage j = k-3:  tau = b.db/(|b|^2 + eps) = s_j B_j.(B_{j+1} - B_{j-1}) / (|B_j|^2 + 64 eps)   (ref:91-95)
@@ -460,7 +493,7 @@ __device__ __forceinline__ unsigned finalize_grouped(const Sums& A, const int n,
     out[6 * S + s] = A.en;
     out[7 * S + s] = (n >= 4) ? A.ta * rn : 0.0;                           // ref:86-87,96
     out[8 * S + s] = A.th / (double)(n - 2);                               // ref:106
-    out[9 * S + s] = ((A.mx0 - A.mn0) * (A.mx1 - A.mn1)) * (A.mx2 - A.mn2);   // ref:117
+    out[9 * S + s] = ((key_value(A.mx0) - key_value(A.mn0)) * (key_value(A.mx1) - key_value(A.mn1))) * (key_value(A.mx2) - key_value(A.mn2));   // ref:117
     double g0 = A.q0 * rn, g1 = A.q1 * rn, g2 = A.q2 * rn;                 // centroid - m
     double c00 = fma(-A.q0, g0, A.q00) * rn1, c01 = fma(-A.q0, g1, A.q01) * rn1, c02 = fma(-A.q0, g2, A.q02) * rn1;
     double c11 = fma(-A.q1, g1, A.q11) * rn1, c12 = fma(-A.q1, g2, A.q12) * rn1, c22 = fma(-A.q2, g2, A.q22) * rn1;
@@ -506,22 +539,24 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
     const uint32_t stage_dst0 = ring_u32 + (lane >> 3) * kRingStride + part * 16;
     const uint4* stage_desc = desc + (lane >> 3);
 
-    // dynamic group queue: the first round of groups is static, later ones come from a global ticket
+    // dynamic group queue: the first group of a warp is static, later ones come from a global ticket.
+    // Two-deep software pipeline: the ticket for the group after next is taken while the record of the
+    // next group is being fetched, so neither latency is exposed.
     int64_t g = (int64_t)blockIdx.x * kWarpsPerCta + warp;
     uint4 rec = make_uint4(0u, 0u, 0u, 0u);
     if (g < n_groups && (g << 5) + lane < M) rec = __ldg(queue + (g << 5) + lane);
+    int64_t gn = 0;
+    if (lane == 0) gn = warps_total + (int64_t)atomicAdd(ticket, 1ull);
+    gn = __shfl_sync(0xffffffffu, gn, 0);
 
     while (g < n_groups) {
         const bool act = (g << 5) + lane < M;
         const int64_t o0 = (int64_t)(((uint64_t)rec.y << 32) | (uint64_t)rec.x);
         const int n = act ? (int)rec.z : 0;
         const int64_t s = (int64_t)rec.w;
-        // take the next ticket and prefetch that group's queue record: the latency of both hides
-        // behind this group's streaming
-        int64_t gn = 0;
-        if (lane == 0) gn = warps_total + (int64_t)atomicAdd(ticket, 1ull);
-        gn = __shfl_sync(0xffffffffu, gn, 0);
-        if (gn < n_groups && (gn << 5) + lane < M) rec = __ldg(queue + (gn << 5) + lane);
+        if (gn < n_groups && (gn << 5) + lane < M) rec = __ldg(queue + (gn << 5) + lane);   // used by the next iteration
+        unsigned long long tk = 0ull;
+        if (lane == 0) tk = atomicAdd(ticket, 1ull);                                          // used at the end of this one
         const double* base = xyz + 3 * o0;
         const uint64_t baddr = (uint64_t)(uintptr_t)base;
         const int skew = act ? (int)(baddr & 31u) : 0;                 // 0, 8, 16 or 24
@@ -535,7 +570,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
         if (act && a0 < xyz_lo) { ok = false; total = 0u; }   // would read below the array (unaligned xyz): exact path
         desc[lane] = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), total, 0u);
         const int n0 = __shfl_sync(0xffffffffu, n, 0);
-        const bool exact = __all_sync(0xffffffffu, act && n == n0) && n0 >= 8;
+        const bool exact = __all_sync(0xffffffffu, act && n == n0) && n0 >= kHead + 2;
         int nmax = n;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
@@ -554,8 +589,8 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
                 const int rem = (int)d.z - pos0;
                 const uint32_t dst = dst0 + i * (4 * kRingStride);
                 cp_async16_if<0, 0>(dst, src, rem, l2_stream);
-                cp_async16_if<128, 128>(dst, src, rem, l2_stream);
-                if (part < kPieces - 16) cp_async16_if<256, 256>(dst, src, rem, l2_stream);
+                if (kPieces > 16 || part < kPieces - 8) cp_async16_if<128, 128>(dst, src, rem, l2_stream);
+                if (kPieces > 16 && part < kPieces - 16) cp_async16_if<256, 256>(dst, src, rem, l2_stream);
             }
             cp_async_commit();
         };
@@ -571,7 +606,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
             // ---- all 32 polylines have n0 >= 8 points: every step is warp-uniform.
             //      head k = 0..5 and tail k = n0..n0+2 are compile-time specialisations of the EDGE step
             //      (every predicate folds), the interior runs the predicate-free STEADY step.
-            __builtin_assume(n0 >= 8);
+            __builtin_assume(n0 >= kHead + 2);
             const int rounds_e = (n0 + kChunk - 1) / kChunk;           // rounds that bring in points
 #pragma unroll 1
             for (int q = 0; q < rounds_e; ++q) {
@@ -583,12 +618,12 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
                 if (q == 0) {
                     const double* pp = (const double*)slot;
 #pragma unroll
-                    for (int k = 0; k < 6; ++k) {
+                    for (int k = 0; k < kHead; ++k) {
                         cx = pp[3 * k]; cy = pp[3 * k + 1]; cz = pp[3 * k + 2];
                         if (k == 0) { m0 = cx; m1 = cy; m2 = cz; }
                         lane_step<EDGE>(k, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
                     }
-                    b = 2;
+                    b = kHead / kSub;
                 }
 #pragma unroll 1
                 for (; b < kChunk / kSub; ++b) {
@@ -660,6 +695,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
         }
         __syncwarp();
         g = gn;
+        gn = warps_total + (int64_t)__shfl_sync(0xffffffffu, tk, 0);
     }
 }
 
