@@ -269,6 +269,15 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// a kernel may raise a word in device memory (+32 in the queue header) to report a failed invariant
+int check_pipeline_error(tg_context* c) {
+    if (!c->d_qhead.p) return TG_OK;
+    int e = 0;
+    TG_CUDA(cudaMemcpy(&e, (char*)c->d_qhead.p + 32, sizeof(int), cudaMemcpyDeviceToHost));
+    if (e != 0) return set_err(TG_E_CUDA, "device pipeline error %s; results are invalid", std::to_string(e).c_str());
+    return TG_OK;
+}
+
 int upload_bundle_src() {
     static thread_local int done_for = -1;
     int dev = -1;
@@ -346,7 +355,7 @@ int tg_synchronize(tg_context* c) {
     if (!c) return set_err(TG_E_INVALID, "null context");
     DeviceGuard g(c->device);
     TG_CUDA(cudaStreamSynchronize(c->stream));
-    return TG_OK;
+    return check_pipeline_error(c);
 }
 
 int tg_stream(tg_context* c, void** stream) {
@@ -389,7 +398,10 @@ static int launch_metrics_f64(tg_context* c, const double* xyz, uint64_t lo, uin
     // queue scratch: [n_long | total | ticket], hist/cursor, start, queue records (+ long ids at the end)
     const int64_t n_windows = (S + tg::kWindow - 1) / tg::kWindow;
     int rc;
-    if ((rc = c->d_qhead.reserve(64))) return rc;
+    if (!c->d_qhead.p) {
+        if ((rc = c->d_qhead.reserve(64))) return rc;
+        TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 64, st));
+    }
     if ((rc = c->d_hist.reserve(sizeof(unsigned) * tg::kBins * (size_t)n_windows))) return rc;
     if ((rc = c->d_start.reserve(sizeof(int64_t) * tg::kBins * (size_t)n_windows))) return rc;
     if ((rc = c->d_perm.reserve(sizeof(uint4) * (size_t)S))) return rc;
@@ -399,7 +411,7 @@ static int launch_metrics_f64(tg_context* c, const double* xyz, uint64_t lo, uin
     unsigned* d_hist = (unsigned*)c->d_hist.p;
     int64_t* d_start = (int64_t*)c->d_start.p;
     uint4* d_queue = (uint4*)c->d_perm.p;
-    TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 64, st));
+    TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 32, st));          // n_long, total, ticket (the pipeline error word at +32 is sticky)
     TG_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * tg::kBins * (size_t)n_windows, st));
     const unsigned seg_grid = (unsigned)((S + tg::kBinSeg - 1) / tg::kBinSeg);
     tg::k_bin_count<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist);
@@ -408,7 +420,9 @@ static int launch_metrics_f64(tg_context* c, const double* xyz, uint64_t lo, uin
     const int64_t groups = (S + 31) / 32;
     const int64_t ctas = (groups + tg::kWarpsPerCta - 1) / tg::kWarpsPerCta;
     const unsigned grid = (unsigned)(ctas < c->sm_count ? ctas : c->sm_count);
-    tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>(xyz, lo, hi, ld, d_queue, d_total, d_ticket, d_out, d_keep);
+    {
+        tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>(xyz, lo, hi, ld, d_queue, d_total, d_ticket, d_out, d_keep);
+    }
     tg::k_metrics_long<<<(unsigned)c->sm_count * 4u, tg::kLongThreads, 0, st>>>(xyz, d_offsets, ld, (const unsigned*)(d_queue + S), d_nlong, d_out, d_keep);
     c->launches += 5;
     TG_CUDA(cudaGetLastError());
@@ -587,7 +601,7 @@ int tg_metrics_csr_host(tg_context* c, const void* h_xyz, int xyz_dtype, const i
     TG_CUDA(cudaStreamSynchronize(c->s_copy));
     TG_CUDA(cudaStreamSynchronize(st));
     TG_CUDA(cudaStreamSynchronize(c->s_back));
-    return TG_OK;
+    return check_pipeline_error(c);
 }
 
 }  // extern "C"
