@@ -207,3 +207,44 @@ def test_chunked_host_pipeline_equals_single_shot(gpu_ctx, monkeypatch):
     ref_sl, _ = so.compute_streamline_metrics_csr(pts, off)
     out, keep, _, _ = gpu_ctx.metrics_host(pts, off)
     assert_table_close(out[:, keep == 3].T, ref_sl.to_numpy(), "chunked+long")
+
+
+def test_config2_batch_of_64_bundles(gpu_ctx):
+    """BASELINE configs[1]: 16 tracts x 4 timepoints, ~5k polylines each, ONE batched call.
+    Every bundle's n_streamlines is exact; three bundles are checked row by row against the oracle."""
+    pts, off, bo = synth.config2(S=5000)
+    assert len(bo) == 65 and len(off) - 1 == 320_000
+    res = tgp.compute_bundles_csr(pts, off, bo, ctx=gpu_ctx)
+    assert len(res) == 64
+    for b, (df_sl, df_b) in enumerate(res):
+        assert len(df_sl) == 5000 and int(df_b["n_streamlines"].iloc[0]) == 5000
+    for b in (0, 37, 63):
+        lo, hi = int(bo[b]), int(bo[b + 1])
+        p, o = pts[off[lo]:off[hi]], off[lo:hi + 1] - off[lo]
+        ref_sl, ref_b = so.compute_streamline_metrics_csr(p[:int(o[600])], o[:601])     # first 600 rows of the bundle
+        assert_table_close(res[b][0].to_numpy()[:600], ref_sl.to_numpy(), f"bundle{b}")
+        # bundle means: against the oracle's nan-mean over OUR full table (the aggregate itself is exact arithmetic)
+        mine = res[b][0]
+        exp = so.bundle_summary(mine).iloc[0].to_numpy(float)
+        assert_bundle_close(res[b][1].iloc[0].to_numpy(float), exp, mine.to_numpy(), f"bundle{b} means")
+
+
+def test_heavy_tail_at_scale_subsample(gpu_ctx):
+    """BASELINE configs[3] law (n = min(5000, floor(10/U))) at 300k polylines on the device: counts exact,
+    the 60 longest polylines (long-polyline kernel, n > 2046) and a random subsample match the oracle."""
+    import torch
+    dev = torch.device("cuda:0")
+    S = 300_000
+    n = synth.torch_lengths("heavy", S, 4, dev)
+    pts, off = synth.torch_random_walk_csr(n, 4, dev)
+    P = pts.shape[0]
+    out = torch.empty((17, S), dtype=torch.float64, device=dev)
+    keep = torch.empty(S, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    gpu_ctx.metrics_dev(pts.data_ptr(), _lib.F64, off.data_ptr(), S, P, out.data_ptr(), keep.data_ptr())
+    gpu_ctx.synchronize()
+    assert int((keep == 3).sum()) == S and int(n.max()) == 5000 and int((n > 2046).sum()) > 100
+    idx = np.unique(np.concatenate([torch.topk(n, 60).indices.cpu().numpy(), np.random.default_rng(1).integers(0, S, 400)]))
+    off_h = off.cpu().numpy()
+    rows = [so.metrics_row(pts[off_h[s]:off_h[s + 1]].cpu().numpy()) for s in idx]
+    assert_table_close(out[:, torch.as_tensor(idx, device=dev)].T.cpu().numpy(), np.asarray(rows), "heavy subsample")
