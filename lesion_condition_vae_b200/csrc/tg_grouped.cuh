@@ -270,15 +270,21 @@ __device__ __forceinline__ void pipe_init(Pipe& S) {
 constexpr int kHi_4em9 = 0x3E312DFE;    // high word of ~4e-9: |Vs|^2 above it <=> 2 eps/|Vs| < 3.3e-8 (second-order term < 1e-14)
 constexpr int kHi_1em8 = 0x3E45798F;    // high word of ~1e-8: |d|^2 above it <=> eps/|d| < 1e-8
 constexpr int kHi_quarter = 0x3FD00000; // high word of 0.25
+// Validity of the speculative path is tracked as ONE unsigned maximum per lane (a VIADDMNMX per test):
+// test i contributes hi(x) - lo_i; the lane is fine iff the maximum stays below kChkSpan.  A value below
+// its lower limit wraps to ~2^32; the common span makes the upper limits lo_i * 2^1023 (>= 9e27).
+constexpr unsigned kChkSpan = (unsigned)(kHi_1e300 - kHi_1em8);
+__device__ __forceinline__ unsigned chk_range(double x, int lo_hi) { return (unsigned)(__double2hiint(x) - lo_hi); }
+__device__ __forceinline__ unsigned chk_below(double x, int lim_hi) { return (unsigned)(__double2hiint(x) - lim_hi) + kChkSpan; }   // x > 0 and hi(x) < lim
 
 enum StepMode { STEADY = 0, MASKED = 1, EDGE = 2 };
 
 // ---- stage arithmetic, shared by the three modes (operation for operation) -------------------
-struct SegOut { double len, u, ux, uy, uz; bool ok; };
+struct SegOut { double len, u, ux, uy, uz; unsigned chk; };
 __device__ __forceinline__ SegOut seg_math(const double dx, const double dy, const double dz) {
     SegOut o;
     const double x2 = fma(dz, dz, fma(dy, dy, dx * dx));
-    o.ok = hi_in_range(x2, kHi_1em8, kHi_1e300);
+    o.chk = chk_range(x2, kHi_1em8);
     const double y = rsqrt_fast(x2);                 // 1/|d| to 2^-58
     o.len = x2 * y;
     o.u = kEps * y;                                  // eps/|d| < 1e-8
@@ -289,11 +295,11 @@ __device__ __forceinline__ SegOut seg_math(const double dx, const double dy, con
 // theta = arccos(clip(t.t')) of the eps-biased unit vectors (ref:103-105), as 2 asin(sqrt(Z)/2) with
 // Z/4 = |t'-t|^2/4 + ((1-|t|^2) + (1-|t'|^2))/4 = (1 - t.t')/2
 __device__ __forceinline__ double angle_math(const SegOut& s, const double tx, const double ty, const double tz,
-                                             const double u_prev, bool& ok) {
+                                             const double u_prev, unsigned& chk) {
     const double ex = s.ux - tx, ey = s.uy - ty, ez = s.uz - tz;
     const double dd = fma(ez, ez, fma(ey, ey, ex * ex));
     const double Z = fma(2.0, s.u + u_prev, dd);     // 4 sin^2(theta/2)
-    ok = __double2hiint(Z) < kHi_quarter;
+    chk = chk_below(Z, kHi_quarter);
     const double yz = mufu_rsqrt(Z);                 // quadratic step: 1.3e-12 relative on theta
     const double tz_ = Z * yz;
     const double ez_ = fma(-tz_, yz, 1.0);
@@ -303,10 +309,10 @@ __device__ __forceinline__ double angle_math(const SegOut& s, const double tx, c
     return fma(sZ, w, sZ);
 }
 // kappa_j = |b_j| / (|v_j| + eps)^3 = |B_j| / (|Vs_j| + 2 eps)^3 = |B|^2 rsqrt(|Vs|^6 |B|^2) (1 - 6 eps/|Vs| + ...)   ref:57-59
-__device__ __forceinline__ double kappa_math(const double vax, const double vay, const double vaz, const double bbn, bool& ok) {
+__device__ __forceinline__ double kappa_math(const double vax, const double vay, const double vaz, const double bbn, unsigned& chk) {
     const double vv = fma(vaz, vaz, fma(vay, vay, vax * vax));     // |Vs_j|^2 = 4 |v_j|^2
     const double w = (vv * vv) * (vv * bbn);                       // |Vs|^6 |B|^2
-    ok = hi_in_range(w, kHi_1em280, kHi_1e300) && hi_in_range(vv, kHi_4em9, kHi_1e300);
+    chk = max(chk_range(w, kHi_1em280), chk_range(vv, kHi_4em9));
     double r = mufu_rsqrt(w);
     const double yv = mufu_rsqrt(vv);                              // ~1/|Vs|: 20 bits is plenty for the 1e-11 term
     const double t = w * r;
@@ -321,10 +327,10 @@ __device__ __forceinline__ double kappa_math(const double vax, const double vay,
 // STEADY: the caller guarantees 4 <= k <= n-1 (every stage live, no end effects).
 // EDGE  : 0 <= k <= n+2, k and n warp-uniform; the caller passes P(min(k, n-1)).
 // MASKED: any k (k < 0 or k > n+2: no effect); the caller passes P(clamp(k, 0, n-1)) once k >= 0.
-// `ok` stays true only while every shortcut is valid for this lane's data.
+// `bad` (see kChkSpan) stays below kChkSpan only while every shortcut is valid for this lane's data.
 template <int MODE>
 __device__ __forceinline__ void lane_step(const int k, const int n, const double cx, const double cy, const double cz,
-                                          const double m0, const double m1, const double m2, Pipe& S, Sums& A, bool& ok) {
+                                          const double m0, const double m1, const double m2, Pipe& S, Sums& A, unsigned& bad) {
     const int last = n - 1;
     const bool pP = MODE == STEADY || (k >= 0 && k <= last);          // point stage live
     const bool pS = MODE == STEADY || (k >= 1 && k <= last);          // segment j = k-1
@@ -357,7 +363,7 @@ __device__ __forceinline__ void lane_step(const int k, const int n, const double
     double len_cur = 0.0;
     if (MODE != EDGE || pS) {
         const SegOut s = seg_math(cx - S.p1x, cy - S.p1y, cz - S.p1z);
-        ok = ok && (!pS || s.ok);
+        bad = max(bad, (MODE == MASKED && !pS) ? 0u : s.chk);
         len_cur = s.len;
         if (MODE == MASKED) {
             A.L += sel(pS, s.len, 0.0);
@@ -369,9 +375,9 @@ __device__ __forceinline__ void lane_step(const int k, const int n, const double
             A.t0 += s.ux; A.t1 += s.uy; A.t2 += s.uz;
         }
         if (MODE != EDGE || pA) {
-            bool aok;
-            const double theta = angle_math(s, S.tx, S.ty, S.tz, S.u_prev, aok);
-            ok = ok && (!pA || aok);
+            unsigned achk;
+            const double theta = angle_math(s, S.tx, S.ty, S.tz, S.u_prev, achk);
+            bad = max(bad, (MODE == MASKED && !pA) ? 0u : achk);
             A.th += (MODE == MASKED) ? sel(pA, theta, 0.0) : theta;
         }
         S.tx = s.ux; S.ty = s.uy; S.tz = s.uz; S.u_prev = s.u;   // stale values past the ends are never read
@@ -401,9 +407,9 @@ __device__ __forceinline__ void lane_step(const int k, const int n, const double
             x *= f; y *= f; z *= f;
         }
         const double bb = fma(z, z, fma(y, y, x * x));
-        bool kok;
-        const double kappa = kappa_math(S.vax, S.vay, S.vaz, bb, kok);     // finite on the speculative path
-        ok = ok && (!pB || kok);
+        unsigned kchk;
+        const double kappa = kappa_math(S.vax, S.vay, S.vaz, bb, kchk);    // finite on the speculative path
+        bad = max(bad, (MODE == MASKED && !pB) ? 0u : kchk);
         if (MODE != STEADY && k == 2) A.kK = kappa;                        // shift for the moments: kappa_0
         double dk = kappa - A.kK;
         double kk = kappa * kappa;                                         // ref:77,82-83: kappa^2 (|d_j| + eps)
@@ -565,9 +571,9 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
         // would read past the end of the point array (only the last polyline can): that one is
         // left to the exact path, which reads with plain 8-byte loads
         uint32_t total = act ? (uint32_t)((skew + 24 * n + 15) & ~15) : 0u;
-        bool ok = true;
-        if (act && a0 + total > xyz_end) { ok = false; total -= 16u; }
-        if (act && a0 < xyz_lo) { ok = false; total = 0u; }   // would read below the array (unaligned xyz): exact path
+        unsigned bad = 0u;
+        if (act && a0 + total > xyz_end) { bad = ~0u; total -= 16u; }
+        if (act && a0 < xyz_lo) { bad = ~0u; total = 0u; }   // would read below the array (unaligned xyz): exact path
         desc[lane] = make_uint4((uint32_t)a0, (uint32_t)(a0 >> 32), total, 0u);
         const int n0 = __shfl_sync(0xffffffffu, n, 0);
         const bool exact = __all_sync(0xffffffffu, act && n == n0) && n0 >= kHead + 2;
@@ -621,7 +627,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
                     for (int k = 0; k < kHead; ++k) {
                         cx = pp[3 * k]; cy = pp[3 * k + 1]; cz = pp[3 * k + 2];
                         if (k == 0) { m0 = cx; m1 = cy; m2 = cz; }
-                        lane_step<EDGE>(k, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
+                        lane_step<EDGE>(k, n0, cx, cy, cz, m0, m1, m2, Q, A, bad);
                     }
                     b = kHead / kSub;
                 }
@@ -633,14 +639,14 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
 #pragma unroll
                         for (int i = 0; i < kSub; ++i) {
                             cx = pp[3 * i]; cy = pp[3 * i + 1]; cz = pp[3 * i + 2];
-                            lane_step<STEADY>(k0 + i, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
+                            lane_step<STEADY>(k0 + i, n0, cx, cy, cz, m0, m1, m2, Q, A, bad);
                         }
                     } else {
                         // the last 0..2 interior points
 #pragma unroll 1
                         for (int k = k0; k < n0; ++k) {
                             cx = pp[3 * (k - k0)]; cy = pp[3 * (k - k0) + 1]; cz = pp[3 * (k - k0) + 2];
-                            lane_step<STEADY>(k, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
+                            lane_step<STEADY>(k, n0, cx, cy, cz, m0, m1, m2, Q, A, bad);
                         }
                         break;
                     }
@@ -648,9 +654,9 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
                 __syncwarp();
             }
             // drain: (cx,cy,cz) = P(n0-1) held
-            lane_step<EDGE>(n0, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
-            lane_step<EDGE>(n0 + 1, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
-            lane_step<EDGE>(n0 + 2, n0, cx, cy, cz, m0, m1, m2, Q, A, ok);
+            lane_step<EDGE>(n0, n0, cx, cy, cz, m0, m1, m2, Q, A, bad);
+            lane_step<EDGE>(n0 + 1, n0, cx, cy, cz, m0, m1, m2, Q, A, bad);
+            lane_step<EDGE>(n0 + 2, n0, cx, cy, cz, m0, m1, m2, Q, A, bad);
         } else {
 #pragma unroll 1
             for (int q = 0; q < rounds; ++q) {
@@ -669,7 +675,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
 #pragma unroll
                         for (int i = 0; i < kSub; ++i) {
                             cx = pp[3 * i]; cy = pp[3 * i + 1]; cz = pp[3 * i + 2];
-                            lane_step<STEADY>(k0 + i, n, cx, cy, cz, m0, m1, m2, Q, A, ok);
+                            lane_step<STEADY>(k0 + i, n, cx, cy, cz, m0, m1, m2, Q, A, bad);
                         }
                     } else {
 #pragma unroll
@@ -678,7 +684,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
                             const bool ld = act && k < n;
                             cx = sel(ld, pp[3 * i], cx); cy = sel(ld, pp[3 * i + 1], cy); cz = sel(ld, pp[3 * i + 2], cz);
                             if (k == 0) { m0 = cx; m1 = cy; m2 = cz; }
-                            lane_step<MASKED>(k, n, cx, cy, cz, m0, m1, m2, Q, A, ok);
+                            lane_step<MASKED>(k, n, cx, cy, cz, m0, m1, m2, Q, A, bad);
                         }
                     }
                 }
@@ -690,7 +696,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
         if (act) {
             // (m0,m1,m2) = P(0) and (cx,cy,cz) = P(n-1) are still in registers
             const bool fin = finite_d(A.q0) && finite_d(A.q1) && finite_d(A.q2);
-            if (ok && fin) keep[s] = (uint8_t)finalize_grouped(A, n, m0, m1, m2, cx, cy, cz, m0, m1, m2, out, ld, s);
+            if (bad < kChkSpan && fin) keep[s] = (uint8_t)finalize_grouped(A, n, m0, m1, m2, cx, cy, cz, m0, m1, m2, out, ld, s);
             else keep[s] = (uint8_t)slow_polyline(base, n, out, ld, s);
         }
         __syncwarp();
