@@ -49,6 +49,9 @@
 
 namespace tg {
 
+#ifndef TG_OUT_EVICT_LAST
+#define TG_OUT_EVICT_LAST 1
+#endif
 #ifndef TG_WARPS
 #define TG_WARPS 8
 #endif
@@ -64,6 +67,7 @@ constexpr int kChunk = TG_CHUNK;              // points per ring slot (even, mul
 constexpr int kSub = TG_SUB;                  // steps per unrolled sub-block (3 = rotation period of the pipeline registers)
 constexpr int kHead = ((6 + kSub - 1) / kSub) * kSub;   // first steps of a polyline, run as specialised EDGE steps (>= 4 needed)
 static_assert(kChunk % kSub == 0 && kChunk % 2 == 0 && kHead <= kChunk, "chunk / sub-block geometry");
+static_assert(kChunk == 12, "stage_chunk issues exactly 2-3 pieces per lane: 18/20 pieces per slot");
 constexpr int kChunkBytes = kChunk * 24;      // 288
 constexpr int kSlotBytes = kChunkBytes + 32;  // one 32-byte sector of lead-out: a point never straddles two slots
 constexpr int kRingStride = 2 * kSlotBytes + 16;   // 656 B per lane: 16-B aligned, 2-way bank conflicts at worst
@@ -93,6 +97,20 @@ __device__ __forceinline__ uint64_t policy_evict_first() {
     uint64_t p;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
     return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+// result store that asks L2 to keep the line: the 8-byte stores of a window's polylines land in random
+// order, and a line evicted before its four sectors are complete costs a partial write plus a fill
+__device__ __forceinline__ void st_keep(double* p, double v, uint64_t policy) {
+#if TG_OUT_EVICT_LAST
+    asm volatile("st.global.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(p), "d"(v), "l"(policy) : "memory");
+#else
+    *p = v;
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -479,42 +497,42 @@ __device__ __forceinline__ unsigned finalize_grouped(const Sums& A, const int n,
                                                      const double f0, const double f1, const double f2,
                                                      const double e0, const double e1, const double e2,
                                                      const double m0, const double m1, const double m2,
-                                                     double* __restrict__ out, const int64_t S, const int64_t s) {
+                                                     double* __restrict__ out, const int64_t S, const int64_t s, const uint64_t pol) {
     const double inf = __longlong_as_double(0x7ff0000000000000LL);
     const double dn = (double)n;
     const double rn = rcp_fast(dn), rn1 = rcp_fast(dn - 1.0);             // 1/n, 1/(n-1) to 2^-58
     const double L = A.L;                                                  // > 1e-4 (n-1) on this path: ref:160 passes
     double cx = e0 - f0, cy = e1 - f1, cz = e2 - f2;
     double chord = sqrt(cx * cx + cy * cy + cz * cz);                      // ref:36
-    out[0 * S + s] = L;
-    out[1 * S + s] = chord;
-    out[2 * S + s] = L / fmax(chord, kMinLen);                             // ref:38-41
-    out[3 * S + s] = chord / fmax(L, kMinLen);                             // ref:43-46
+    st_keep(out + 0 * S + s, L, pol);
+    st_keep(out + 1 * S + s, chord, pol);
+    st_keep(out + 2 * S + s, L / fmax(chord, kMinLen), pol);                             // ref:38-41
+    st_keep(out + 3 * S + s, chord / fmax(L, kMinLen), pol);                             // ref:43-46
     {                                                                      // ref:61,71: all n curvatures are finite here
         double dm = A.k1 * rn;
         double m2c = A.k2 - A.k1 * dm;
-        out[4 * S + s] = A.kK + dm;
-        out[5 * S + s] = sqrt(fmax(m2c, 0.0) * rn);
+        st_keep(out + 4 * S + s, A.kK + dm, pol);
+        st_keep(out + 5 * S + s, sqrt(fmax(m2c, 0.0) * rn), pol);
     }
-    out[6 * S + s] = A.en;
-    out[7 * S + s] = (n >= 4) ? A.ta * rn : 0.0;                           // ref:86-87,96
-    out[8 * S + s] = A.th / (double)(n - 2);                               // ref:106
-    out[9 * S + s] = ((key_value(A.mx0) - key_value(A.mn0)) * (key_value(A.mx1) - key_value(A.mn1))) * (key_value(A.mx2) - key_value(A.mn2));   // ref:117
+    st_keep(out + 6 * S + s, A.en, pol);
+    st_keep(out + 7 * S + s, (n >= 4) ? A.ta * rn : 0.0, pol);                           // ref:86-87,96
+    st_keep(out + 8 * S + s, A.th / (double)(n - 2), pol);                               // ref:106
+    st_keep(out + 9 * S + s, ((key_value(A.mx0) - key_value(A.mn0)) * (key_value(A.mx1) - key_value(A.mn1))) * (key_value(A.mx2) - key_value(A.mn2)), pol);   // ref:117
     double g0 = A.q0 * rn, g1 = A.q1 * rn, g2 = A.q2 * rn;                 // centroid - m
     double c00 = fma(-A.q0, g0, A.q00) * rn1, c01 = fma(-A.q0, g1, A.q01) * rn1, c02 = fma(-A.q0, g2, A.q02) * rn1;
     double c11 = fma(-A.q1, g1, A.q11) * rn1, c12 = fma(-A.q1, g2, A.q12) * rn1, c22 = fma(-A.q2, g2, A.q22) * rn1;
     double l1, l2, l3;
     sym3_eigenvalues(c00, c01, c02, c11, c12, c22, l1, l2, l3);
-    out[10 * S + s] = (l2 <= kEps) ? inf : l1 / l2;                        // ref:126-130
-    out[11 * S + s] = (l3 <= kEps) ? inf : l2 / l3;                        // ref:132-136
-    out[12 * S + s] = l1 / (((l1 + l2) + l3) + kEps);                      // ref:138-141
-    out[13 * S + s] = m0 + g0;                                             // ref:183-185
-    out[14 * S + s] = m1 + g1;
-    out[15 * S + s] = m2 + g2;
+    st_keep(out + 10 * S + s, (l2 <= kEps) ? inf : l1 / l2, pol);                        // ref:126-130
+    st_keep(out + 11 * S + s, (l3 <= kEps) ? inf : l2 / l3, pol);                        // ref:132-136
+    st_keep(out + 12 * S + s, l1 / (((l1 + l2) + l3) + kEps), pol);                      // ref:138-141
+    st_keep(out + 13 * S + s, m0 + g0, pol);                                             // ref:183-185
+    st_keep(out + 14 * S + s, m1 + g1, pol);
+    st_keep(out + 15 * S + s, m2 + g2, pol);
     // ref:143-148: mean |t - tbar|^2 = mean |t|^2 - |tbar|^2, mean |t|^2 = 1 - 2 su/(n-1)
     double a0 = A.t0 * rn1, a1 = A.t1 * rn1, a2 = A.t2 * rn1;
     double disp = (1.0 - (a0 * a0 + a1 * a1 + a2 * a2)) - 2.0 * A.su * rn1;
-    out[16 * S + s] = fmax(disp, 0.0);
+    st_keep(out + 16 * S + s, fmax(disp, 0.0), pol);
     return 3u;
 }
 
@@ -536,6 +554,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
     const unsigned char* my_ring = ring + lane * kRingStride;
     const uint64_t xyz_end = xyz_hi;
     const uint64_t l2_stream = policy_evict_first();
+    const uint64_t l2_keep = policy_evict_last();
 
     const int64_t M = *queue_len;
     const int64_t n_groups = (M + 31) >> 5;
@@ -585,9 +604,14 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
         __syncwarp();
 
         // cooperative stage of chunk q of all 32 polylines into slot q&1: 8 lanes per polyline
+        // Slot layout: [0,32) carry | [32,320) fresh.  Chunk 0 is staged whole; for q >= 1 only the 288 fresh
+        // bytes come from memory (whole sectors, every byte fetched once) and the first sector is the previous
+        // slot's last one, copied by the lane itself inside shared memory (carry_sector).
         auto stage_chunk = [&](const int q) {
-            const int pos0 = q * kChunkBytes + part * 16;              // byte position in the aligned stream
-            const uint32_t dst0 = stage_dst0 + (q & 1) * kSlotBytes;
+            const int skip = q > 0 ? 32 : 0;
+            const int pos0 = q * kChunkBytes + skip + part * 16;       // byte position in the aligned stream
+            const uint32_t dst0 = stage_dst0 + (q & 1) * kSlotBytes + skip;
+            const bool third = part < (q > 0 ? kPieces - 18 : kPieces - 16);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const uint4 d = stage_desc[4 * i];
@@ -595,10 +619,16 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
                 const int rem = (int)d.z - pos0;
                 const uint32_t dst = dst0 + i * (4 * kRingStride);
                 cp_async16_if<0, 0>(dst, src, rem, l2_stream);
-                if (kPieces > 16 || part < kPieces - 8) cp_async16_if<128, 128>(dst, src, rem, l2_stream);
-                if (kPieces > 16 && part < kPieces - 16) cp_async16_if<256, 256>(dst, src, rem, l2_stream);
+                cp_async16_if<128, 128>(dst, src, rem, l2_stream);
+                if (third) cp_async16_if<256, 256>(dst, src, rem, l2_stream);
             }
             cp_async_commit();
+        };
+        auto carry_sector = [&](const int q) {                         // end of round q: lead-out of slot q -> head of slot q+1
+            const uint4* src = (const uint4*)(my_ring + (q & 1) * kSlotBytes + kChunkBytes);
+            uint4* dst = (uint4*)(const_cast<unsigned char*>(my_ring) + ((q + 1) & 1) * kSlotBytes);
+            const uint4 v0 = src[0], v1 = src[1];
+            dst[0] = v0; dst[1] = v1;
         };
 
         Sums A;
@@ -651,6 +681,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
                         break;
                     }
                 }
+                if (q + 1 < rounds_e) carry_sector(q);
                 __syncwarp();
             }
             // drain: (cx,cy,cz) = P(n0-1) held
@@ -688,6 +719,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
                         }
                     }
                 }
+                if (q + 1 < rounds) carry_sector(q);
                 __syncwarp();
             }
         }
@@ -696,7 +728,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
         if (act) {
             // (m0,m1,m2) = P(0) and (cx,cy,cz) = P(n-1) are still in registers
             const bool fin = finite_d(A.q0) && finite_d(A.q1) && finite_d(A.q2);
-            if (bad < kChkSpan && fin) keep[s] = (uint8_t)finalize_grouped(A, n, m0, m1, m2, cx, cy, cz, m0, m1, m2, out, ld, s);
+            if (bad < kChkSpan && fin) keep[s] = (uint8_t)finalize_grouped(A, n, m0, m1, m2, cx, cy, cz, m0, m1, m2, out, ld, s, l2_keep);
             else keep[s] = (uint8_t)slow_polyline(base, n, out, ld, s);
         }
         __syncwarp();
