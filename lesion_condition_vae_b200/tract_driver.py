@@ -1,0 +1,243 @@
+"""Batched tract-geometry driver: the B200-first form of the reference's
+``src/geometry/comprehensive_tract_geometry_analysis.py``.
+
+The reference walks groups x subjects x timepoints x 16 tracts serially
+(comprehensive_tract_geometry_analysis.py:169-195), gunzips every ``.vtk.gz`` to a sibling file
+(:54-76) and calls ``compute_streamline_metrics(path, max_streamlines)`` once per file (:102) —
+2,368 calls per run.  Here the files of a batch (default: everything) are parsed into ONE CSR
+tractogram with a bundle table, the ``max_streamlines`` prefix rule is resolved on the host, and
+the metrics + bundle reduction run as ONE device call (``compute_bundles`` hook); ``.gz`` is read
+from memory.  The result is the same DataFrame / CSV: one row per tract file that produced at
+least one streamline, 14 bundle columns in the reference order followed by ``subject_id,
+timepoint, tract, group`` (:109-115), rows in the reference's loop order, ``n_streamlines`` as
+float (the reference passes the summary through ``Series.to_dict``, :109).
+
+Same public names as the reference module: ``TRACT_LIST``, ``load_config``, ``get_all_subjects``,
+``process_single_tract``, ``process_all_tracts``, ``generate_summary_statistics``, ``main``.
+"""
+from __future__ import annotations
+
+import json
+from pathlib import Path
+from typing import Callable, Optional
+
+import numpy as np
+import pandas as pd
+
+from . import vtk_io
+from .tract_geom_proc import BUNDLE_COLUMNS
+
+TRACT_LIST = [  # comprehensive_tract_geometry_analysis.py:25-32
+    'chip_right', 'hipcom', 'thalsub_left',
+    'cing_left', 'thalsub_right',
+    'cing_right',
+    'fimbria_left', 'ant_comm', 'fimbria_right',
+    'atr_left', 'fornix_left', 'intcap_left',
+    'atr_right', 'chip_left', 'fornix_right', 'intcap_right'
+]
+TIMEPOINTS = ['2d', '9d', '1mo', '5mo']  # :162
+META_COLUMNS = ('subject_id', 'timepoint', 'tract', 'group')  # :112-115
+
+
+def load_config(config_path=None):
+    """Tract configuration with subject metadata.  The reference looks for
+    ``<module dir>/lesion_vae_analysis/configs/tract_config.json`` (:36), a path that does not exist
+    in its own tree; here the path is an argument, defaulting to ``configs/tract_config.json``
+    two levels above the package when present."""
+    if config_path is None:
+        for cand in (Path.cwd() / "configs" / "tract_config.json",
+                     Path(__file__).resolve().parent.parent / "configs" / "tract_config.json"):
+            if cand.exists():
+                config_path = cand
+                break
+        else:
+            raise FileNotFoundError("tract_config.json not found; pass config_path")
+    with open(config_path, 'r') as f:
+        return json.load(f)
+
+
+def get_all_subjects(config):
+    """:41-51 — {group: [subject id strings]} for Sham, TBI, PTE, in config order."""
+    out = {}
+    for group, subject_list in config.get('groups', {}).items():
+        if group in ['Sham', 'TBI', 'PTE']:
+            out[group] = [str(s) for s in subject_list]
+    return out
+
+
+def find_tract_file(data_dir, subject_id, timepoint, tract_name):
+    """:86-93 — ``<data>/<subject>/<timepoint>/bundles/<tract>_curves.vtk.gz``, else without ``.gz``."""
+    base = Path(data_dir) / subject_id / timepoint / "bundles"
+    for name in (f"{tract_name}_curves.vtk.gz", f"{tract_name}_curves.vtk"):
+        p = base / name
+        if p.exists():
+            return p
+    return None
+
+
+def select_prefix(points, offsets, max_streamlines):
+    """The loader rule of tract_geom_proc.py:17-25 on a CSR tractogram, vectorised: indices of the
+    polylines with more than 2 points and only finite coordinates, in file order, cut after
+    ``max_streamlines`` of them (the cap is tested after an append, so a cap <= 0 still admits one)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n = np.diff(offsets)
+    S = len(n)
+    if S == 0:
+        return np.zeros(0, dtype=np.int64)
+    bad_pt = ~np.isfinite(points).all(axis=1) if len(points) else np.zeros(0, bool)
+    csum = np.concatenate([[0], np.cumsum(bad_pt, dtype=np.int64)])
+    bad = (csum[offsets[1:]] - csum[offsets[:-1]]) > 0
+    idx = np.flatnonzero((n > 2) & ~bad)
+    if max_streamlines is not None:
+        idx = idx[:max(int(max_streamlines), 1)]
+    return idx
+
+
+def gather_polylines(points, offsets, idx):
+    """CSR of the selected polylines (contiguous copy)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    n = offsets[idx + 1] - offsets[idx]
+    new_off = np.zeros(len(idx) + 1, dtype=np.int64)
+    np.cumsum(n, out=new_off[1:])
+    if len(idx) and np.array_equal(idx, np.arange(idx[0], idx[0] + len(idx))):
+        return points[offsets[idx[0]]:offsets[idx[-1] + 1]], new_off          # a contiguous run: a view
+    rows = np.repeat(offsets[idx] - new_off[:-1], n) + np.arange(int(new_off[-1]), dtype=np.int64)
+    return points[rows], new_off
+
+
+def _default_compute(points, offsets, bundle_offsets):
+    """One device call for the whole batch -> (n_streamlines int64[B], means float64[B,13])."""
+    from . import _lib
+    ctx = _lib.default_context()
+    _, _, sums, counts = ctx.metrics_host(points, offsets, bundle_offsets, want_rows=False)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        means = np.where(counts[:, 1:] > 0, sums / np.maximum(counts[:, 1:], 1), np.nan)
+    return counts[:, 0].copy(), means
+
+
+def process_batch(jobs, max_streamlines=None, compute: Optional[Callable] = None, verbose=False):
+    """``jobs`` = list of (subject_id, timepoint, tract_name, group, path).  Returns one metrics dict per
+    job, or None where the reference would have skipped the tract (unreadable file, :129-131, or no
+    surviving streamline, which raises KeyError('length') inside the reference's hot path)."""
+    compute = compute or _default_compute
+    P, O, B, live = [], [np.zeros(1, np.int64)], [0], []
+    base = 0
+    dtype = None
+    for j, (_, _, tract, _, path) in enumerate(jobs):
+        try:
+            pts, off = vtk_io.read_polylines_csr(path)
+        except Exception as e:  # the reference prints and skips (:129-131)
+            if verbose:
+                print(f"      [ERROR] Failed to process {tract}: {e}")
+            continue
+        idx = select_prefix(pts, off, max_streamlines)
+        if len(idx) == 0:
+            if verbose:
+                print(f"      [ERROR] Failed to process {tract}: 'length'")
+            continue
+        p, o = gather_polylines(pts, off, idx)
+        dtype = p.dtype if dtype is None else np.result_type(dtype, p.dtype)
+        P.append(p); O.append(o[1:] + base); base += int(o[-1]); B.append(B[-1] + len(idx)); live.append(j)
+    results = [None] * len(jobs)
+    if not live:
+        return results
+    points = np.concatenate([np.asarray(p, dtype=dtype) for p in P]) if len(P) > 1 else np.ascontiguousarray(P[0], dtype=dtype)
+    n_sl, means = compute(points, np.concatenate(O), np.asarray(B, dtype=np.int64))
+    for b, j in enumerate(live):
+        subject_id, timepoint, tract, group, _ = jobs[j]
+        if n_sl[b] == 0:                               # every selected polyline had length <= 1e-8
+            if verbose:
+                print(f"      [ERROR] Failed to process {tract}: 'length'")
+            continue
+        m = {"n_streamlines": float(n_sl[b])}          # Series.to_dict of a mixed int/float row gives floats (:109)
+        for name, v in zip(BUNDLE_COLUMNS[1:], means[b]):
+            m[name] = float(v)
+        m['subject_id'] = subject_id; m['timepoint'] = timepoint; m['tract'] = tract; m['group'] = group
+        results[j] = m
+        if verbose:
+            print(f"      ✓ {tract}: {m['n_streamlines']} streamlines, length={m['length_mean']:.1f}mm")
+    return results
+
+
+def process_single_tract(subject_id, timepoint, tract_name, data_dir, group, max_streamlines=None, compute=None):
+    """:79-131 — one tract -> metrics dict or None."""
+    path = find_tract_file(Path(data_dir), subject_id, timepoint, tract_name)
+    if path is None:
+        return None
+    return process_batch([(subject_id, timepoint, tract_name, group, path)], max_streamlines, compute)[0]
+
+
+def process_all_tracts(config, data_dir, output_dir, max_streamlines=None, compute=None, batch="all", verbose=False):
+    """:134-220 — every tract of every subject and timepoint -> DataFrame (reference row order).
+
+    ``batch``: "all" (one device call for the whole study), "subject" or "timepoint" (one call per
+    subject / per subject x timepoint, for studies that do not fit in host memory at once)."""
+    data_dir, output_dir = Path(data_dir), Path(output_dir)
+    output_dir.mkdir(parents=True, exist_ok=True)
+    jobs, cuts = [], []
+    for group, subjects in get_all_subjects(config).items():
+        for subject_id in sorted(subjects):
+            for timepoint in TIMEPOINTS:
+                for tract in TRACT_LIST:
+                    path = find_tract_file(data_dir, subject_id, timepoint, tract)
+                    if path is not None:
+                        jobs.append((subject_id, timepoint, tract, group, path))
+                if batch == "timepoint":
+                    cuts.append(len(jobs))
+            if batch == "subject":
+                cuts.append(len(jobs))
+    cuts = sorted(set(cuts + [len(jobs)]))
+    results, lo = [], 0
+    for hi in cuts:
+        if hi > lo:
+            results += [m for m in process_batch(jobs[lo:hi], max_streamlines, compute, verbose) if m is not None]
+        lo = hi
+    return pd.DataFrame(results)
+
+
+def generate_summary_statistics(results_df, output_dir):
+    """:223-296 — the two summary CSVs (by group x timepoint, by tract x group)."""
+    output_dir = Path(output_dir)
+    key_metrics = ['length_mean', 'tortuosity_mean', 'curv_mean_avg', 'elongation_ratio_mean', 'planarity_ratio_mean']
+    rows = []
+    for group in sorted(results_df['group'].unique()):
+        for tp in sorted(results_df['timepoint'].unique()):
+            sub = results_df[(results_df['group'] == group) & (results_df['timepoint'] == tp)]
+            if len(sub) > 0:
+                r = {'group': group, 'timepoint': tp, 'n_records': len(sub),
+                     'n_subjects': sub['subject_id'].nunique(), 'n_tracts': sub['tract'].nunique()}
+                for metric in key_metrics:
+                    if metric in sub.columns:
+                        r[f'{metric}_mean'] = sub[metric].mean()
+                        r[f'{metric}_std'] = sub[metric].std()
+                rows.append(r)
+    summary_df = pd.DataFrame(rows)
+    summary_df.to_csv(output_dir / "summary_statistics_by_group_timepoint.csv", index=False)
+    rows = []
+    for tract in sorted(results_df['tract'].unique()):
+        for group in sorted(results_df['group'].unique()):
+            sub = results_df[(results_df['tract'] == tract) & (results_df['group'] == group)]
+            if len(sub) > 0:
+                rows.append({'tract': tract, 'group': group, 'n_records': len(sub),
+                             'length_mean': sub['length_mean'].mean(), 'length_std': sub['length_mean'].std(),
+                             'tortuosity_mean': sub['tortuosity_mean'].mean(), 'tortuosity_std': sub['tortuosity_mean'].std(),
+                             'curv_mean': sub['curv_mean_avg'].mean(), 'curv_std': sub['curv_mean_avg'].std()})
+    tract_summary_df = pd.DataFrame(rows)
+    tract_summary_df.to_csv(output_dir / "summary_statistics_by_tract_group.csv", index=False)
+    return summary_df, tract_summary_df
+
+
+def main(data_dir=None, output_dir=None, config_path=None, max_streamlines=100):
+    """:299-329 — run the study and write ``comprehensive_tract_geometry_metrics.csv`` plus the two
+    summaries.  ``max_streamlines=100`` is the reference's shipped setting (:310); None = all."""
+    root = Path.cwd()
+    data_dir = Path(data_dir) if data_dir else root / "data"
+    output_dir = Path(output_dir) if output_dir else root / "results" / "comprehensive_tract_geometry"
+    config = load_config(config_path)
+    results_df = process_all_tracts(config, data_dir, output_dir, max_streamlines=max_streamlines)
+    if len(results_df) == 0:
+        print("[ERROR] No results to save!")
+        return results_df
+    results_df.to_csv(output_dir / "comprehensive_tract_geometry_metrics.csv", index=False)
+    generate_summary_statistics(results_df, output_dir)
+    return results_df
