@@ -40,9 +40,11 @@ def _check(df, golden_csv):
     assert df["n_streamlines"].dtype == np.float64 and np.array_equal(df["n_streamlines"], ref["n_streamlines"])
     for name, src in zip(list(ref.columns)[1:14], BUNDLE_SOURCE):
         g, r = df[name].to_numpy(float), ref[name].to_numpy(float)
-        # eigen ratios: LAPACK's own error grows with the condition number (parity_rules.py); bundles of
-        # ~12 short polylines here stay far below the level where that matters, so the plain rule applies
-        tol = RTOL * np.abs(r) + ATOL[src]
+        # eigen ratios: LAPACK's own error is ~1e-16 * lambda1/lambda3 (parity_rules.py).  This
+        # study has polylines of 3-6 points (planar or nearly so: lambda1/lambda3 up to ~1e9) and the CSV
+        # holds only bundle means, so the per-row conditioned rule cannot be applied: 1e-6 for these two
+        rtol = 1e-6 if src in ("elongation_ratio", "planarity_ratio") else RTOL
+        tol = rtol * np.abs(r) + ATOL[src]
         bad = ~(np.abs(g - r) <= tol) & ~(np.isnan(g) & np.isnan(r)) & ~(np.isinf(r) & (g == r))
         assert not bad.any(), (name, g[bad][:3], r[bad][:3])
 
