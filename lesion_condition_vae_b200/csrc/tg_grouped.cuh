@@ -154,40 +154,71 @@ k_bin_count(const int64_t* __restrict__ offsets, const int64_t S, unsigned* __re
         if (sh[i] != 0u) atomicAdd(&h[i], sh[i]);
 }
 
-// hist -> exclusive start positions (in place, global over all windows); total[0] = queue length M
+// hist[w] -> exclusive start positions inside window w (one CTA per window); wtotal[w] = polylines queued from window w.
+// hist becomes the scatter cursor (zeroed).
 __global__ void __launch_bounds__(1024)
-k_bin_scan(unsigned* __restrict__ hist, const int64_t n_windows, int64_t* __restrict__ start, int64_t* __restrict__ total) {
+k_bin_scan(unsigned* __restrict__ hist, int64_t* __restrict__ start, int64_t* __restrict__ wtotal) {
     __shared__ unsigned wsum[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t w = blockIdx.x;
+    unsigned* h = hist + w * kBins;
+    const unsigned a = h[2 * threadIdx.x], b = h[2 * threadIdx.x + 1];
+    unsigned v = a + b;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    if (lane == 31) wsum[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        unsigned t = wsum[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned u = __shfl_up_sync(0xffffffffu, t, o);
+            if (lane >= o) t += u;
+        }
+        wsum[lane] = t;
+    }
+    __syncthreads();
+    const int64_t base = (int64_t)(warp ? wsum[warp - 1] : 0u) + (v - (a + b));
+    start[w * kBins + 2 * threadIdx.x] = base;
+    start[w * kBins + 2 * threadIdx.x + 1] = base + a;
+    h[2 * threadIdx.x] = 0u;
+    h[2 * threadIdx.x + 1] = 0u;
+    if (threadIdx.x == 0) wtotal[w] = (int64_t)wsum[31];
+}
+
+// wtotal -> exclusive window bases (in place); total[0] = queue length M.  One CTA; windows are few.
+__global__ void __launch_bounds__(1024)
+k_window_scan(int64_t* __restrict__ wtotal, const int64_t n_windows, int64_t* __restrict__ total) {
+    __shared__ int64_t wsum[32];
     __shared__ int64_t run;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) run = 0;
     __syncthreads();
-    for (int64_t w = 0; w < n_windows; ++w) {
-        unsigned* h = hist + w * kBins;
-        const unsigned a = h[2 * threadIdx.x], b = h[2 * threadIdx.x + 1];
-        unsigned v = a + b;
+    for (int64_t w0 = 0; w0 < n_windows; w0 += 1024) {
+        const int64_t w = w0 + threadIdx.x;
+        const int64_t a = w < n_windows ? wtotal[w] : 0;
+        int64_t v = a;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            unsigned t = __shfl_up_sync(0xffffffffu, v, o);
+            int64_t t = __shfl_up_sync(0xffffffffu, v, o);
             if (lane >= o) v += t;
         }
         if (lane == 31) wsum[warp] = v;
         __syncthreads();
         if (warp == 0) {
-            unsigned t = wsum[lane];
+            int64_t t = wsum[lane];
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                unsigned u = __shfl_up_sync(0xffffffffu, t, o);
+                int64_t u = __shfl_up_sync(0xffffffffu, t, o);
                 if (lane >= o) t += u;
             }
             wsum[lane] = t;
         }
         __syncthreads();
-        const int64_t base = run + (warp ? wsum[warp - 1] : 0u) + (v - (a + b));
-        start[w * kBins + 2 * threadIdx.x] = base;
-        start[w * kBins + 2 * threadIdx.x + 1] = base + a;
-        h[2 * threadIdx.x] = 0u;                      // becomes the scatter cursor
-        h[2 * threadIdx.x + 1] = 0u;
+        if (w < n_windows) wtotal[w] = run + (warp ? wsum[warp - 1] : 0) + (v - a);
         __syncthreads();
         if (threadIdx.x == 0) run += wsum[31];
         __syncthreads();
@@ -200,7 +231,7 @@ k_bin_scan(unsigned* __restrict__ hist, const int64_t n_windows, int64_t* __rest
 // queue buffer (records + ids never exceed its S x 16 bytes) and counted in n_long.
 __global__ void __launch_bounds__(kBinThreads)
 k_bin_scatter(const int64_t* __restrict__ offsets, const int64_t S, unsigned* __restrict__ cursor,
-              const int64_t* __restrict__ start, uint4* __restrict__ queue, double* __restrict__ out,
+              const int64_t* __restrict__ start, const int64_t* __restrict__ wbase, uint4* __restrict__ queue, double* __restrict__ out,
               const int64_t ld, uint8_t* __restrict__ keep, int* __restrict__ n_long) {
     __shared__ unsigned sh[kBins];       // pass 1: count; then: next free rank inside this CTA's reservation
     for (int i = threadIdx.x; i < kBins; i += kBinThreads) sh[i] = 0u;
@@ -230,7 +261,7 @@ k_bin_scatter(const int64_t* __restrict__ offsets, const int64_t S, unsigned* __
         const int64_t n = __ldg(offsets + s + 1) - o0;
         if (n >= 3 && n <= kMaxGroupedN) {
             const unsigned r = atomicAdd(&sh[(int)n], 1u);
-            queue[start[w * kBins + n] + r] = make_uint4((unsigned)o0, (unsigned)((uint64_t)o0 >> 32), (unsigned)n, (unsigned)s);
+            queue[wbase[w] + start[w * kBins + n] + r] = make_uint4((unsigned)o0, (unsigned)((uint64_t)o0 >> 32), (unsigned)n, (unsigned)s);
         }
     }
 }
@@ -607,6 +638,15 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
         // Slot layout: [0,32) carry | [32,320) fresh.  Chunk 0 is staged whole; for q >= 1 only the 288 fresh
         // bytes come from memory (whole sectors, every byte fetched once) and the first sector is the previous
         // slot's last one, copied by the lane itself inside shared memory (carry_sector).
+        // the 8 stream descriptors this lane stages from: fetched once per group, kept in registers
+        uint64_t sd_src[8];
+        int sd_len[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint4 d = stage_desc[4 * i];
+            sd_src[i] = ((uint64_t)d.y << 32) | (uint64_t)d.x;
+            sd_len[i] = (int)d.z;
+        }
         auto stage_chunk = [&](const int q) {
             const int skip = q > 0 ? 32 : 0;
             const int pos0 = q * kChunkBytes + skip + part * 16;       // byte position in the aligned stream
@@ -614,9 +654,8 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
             const bool third = part < (q > 0 ? kPieces - 18 : kPieces - 16);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const uint4 d = stage_desc[4 * i];
-                const unsigned char* src = (const unsigned char*)(uintptr_t)(((uint64_t)d.y << 32) | (uint64_t)d.x) + pos0;
-                const int rem = (int)d.z - pos0;
+                const unsigned char* src = (const unsigned char*)(uintptr_t)sd_src[i] + pos0;
+                const int rem = sd_len[i] - pos0;
                 const uint32_t dst = dst0 + i * (4 * kRingStride);
                 cp_async16_if<0, 0>(dst, src, rem, l2_stream);
                 cp_async16_if<128, 128>(dst, src, rem, l2_stream);

@@ -160,29 +160,34 @@ k_bundle_tiles(const double* __restrict__ out, const uint8_t* __restrict__ keep,
     }
 }
 
-// one warp per bundle; tile_first[b]..tile_first[b+1] are its tiles
-__global__ void __launch_bounds__(32)
+// one CTA per bundle; tile_first[b]..tile_first[b+1] are its tiles.  Thread t adds tiles t, t+256, ... in
+// order, then the 256 partials are added in a fixed tree: the result does not depend on scheduling.
+constexpr int kFinalThreads = 256;
+__global__ void __launch_bounds__(kFinalThreads)
 k_bundle_final(const int64_t* __restrict__ tile_first, const double* __restrict__ tsum, const int64_t* __restrict__ tcnt,
                double* __restrict__ sums, int64_t* __restrict__ counts) {
+    __shared__ double s_v[kFinalThreads];
+    __shared__ long long s_c[kFinalThreads];
     const int64_t b = blockIdx.x;
     const int64_t t0 = tile_first[b], t1 = tile_first[b + 1];
-    const int lane = threadIdx.x;
     for (int j = 0; j < kNB + 1; ++j) {
         double v = 0.0;
-        int64_t c = 0;
-        for (int64_t t = t0 + lane; t < t1; t += 32) {
+        long long c = 0;
+        for (int64_t t = t0 + threadIdx.x; t < t1; t += kFinalThreads) {
             if (j < kNB) v += tsum[t * kNB + j];
             c += tcnt[t * (kNB + 1) + j];
         }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            v += __shfl_down_sync(0xffffffffu, v, o);
-            c += __shfl_down_sync(0xffffffffu, c, o);
+        s_v[threadIdx.x] = v; s_c[threadIdx.x] = c;
+        __syncthreads();
+        for (int o = kFinalThreads / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) { s_v[threadIdx.x] += s_v[threadIdx.x + o]; s_c[threadIdx.x] += s_c[threadIdx.x + o]; }
+            __syncthreads();
         }
-        if (lane == 0) {
-            if (j < kNB) sums[b * kNB + j] = v;
-            counts[b * (kNB + 1) + j] = c;
+        if (threadIdx.x == 0) {
+            if (j < kNB) sums[b * kNB + j] = s_v[0];
+            counts[b * (kNB + 1) + j] = s_c[0];
         }
+        __syncthreads();
     }
 }
 
@@ -403,20 +408,22 @@ static int launch_metrics_f64(tg_context* c, const double* xyz, uint64_t lo, uin
         TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 64, st));
     }
     if ((rc = c->d_hist.reserve(sizeof(unsigned) * tg::kBins * (size_t)n_windows))) return rc;
-    if ((rc = c->d_start.reserve(sizeof(int64_t) * tg::kBins * (size_t)n_windows))) return rc;
+    if ((rc = c->d_start.reserve(sizeof(int64_t) * (tg::kBins + 1) * (size_t)n_windows))) return rc;
     if ((rc = c->d_perm.reserve(sizeof(uint4) * (size_t)S))) return rc;
     int* d_nlong = (int*)c->d_qhead.p;
     int64_t* d_total = (int64_t*)((char*)c->d_qhead.p + 8);
     unsigned long long* d_ticket = (unsigned long long*)((char*)c->d_qhead.p + 16);
     unsigned* d_hist = (unsigned*)c->d_hist.p;
     int64_t* d_start = (int64_t*)c->d_start.p;
+    int64_t* d_wbase = d_start + tg::kBins * n_windows;          // per-window totals, then bases
     uint4* d_queue = (uint4*)c->d_perm.p;
     TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 32, st));          // n_long, total, ticket (the pipeline error word at +32 is sticky)
     TG_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * tg::kBins * (size_t)n_windows, st));
     const unsigned seg_grid = (unsigned)((S + tg::kBinSeg - 1) / tg::kBinSeg);
     tg::k_bin_count<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist);
-    tg::k_bin_scan<<<1, 1024, 0, st>>>(d_hist, n_windows, d_start, d_total);
-    tg::k_bin_scatter<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist, d_start, d_queue, d_out, ld, d_keep, d_nlong);
+    tg::k_bin_scan<<<(unsigned)n_windows, 1024, 0, st>>>(d_hist, d_start, d_wbase);
+    tg::k_window_scan<<<1, 1024, 0, st>>>(d_wbase, n_windows, d_total);
+    tg::k_bin_scatter<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist, d_start, d_wbase, d_queue, d_out, ld, d_keep, d_nlong);
     const int64_t groups = (S + 31) / 32;
     const int64_t ctas = (groups + tg::kWarpsPerCta - 1) / tg::kWarpsPerCta;
     const unsigned grid = (unsigned)(ctas < c->sm_count ? ctas : c->sm_count);
@@ -424,7 +431,7 @@ static int launch_metrics_f64(tg_context* c, const double* xyz, uint64_t lo, uin
         tg::k_metrics_grouped<<<grid, tg::kGroupedThreads, tg::kGroupedSmem, st>>>(xyz, lo, hi, ld, d_queue, d_total, d_ticket, d_out, d_keep);
     }
     tg::k_metrics_long<<<(unsigned)c->sm_count * 4u, tg::kLongThreads, 0, st>>>(xyz, d_offsets, ld, (const unsigned*)(d_queue + S), d_nlong, d_out, d_keep);
-    c->launches += 5;
+    c->launches += 6;
     TG_CUDA(cudaGetLastError());
     return TG_OK;
 }
@@ -505,7 +512,7 @@ int tg_bundle_reduce_dev(tg_context* c, const double* d_out, const uint8_t* d_ke
         tg::k_bundle_tiles<<<(unsigned)nt, tg::kBundleThreads, 0, st>>>(d_out, d_keep, d_select, S, dt, (double*)c->d_tsum.p, (int64_t*)c->d_tcnt.p);
         c->launches += 1;
     }
-    tg::k_bundle_final<<<(unsigned)B, 32, 0, st>>>(df, (const double*)c->d_tsum.p, (const int64_t*)c->d_tcnt.p, d_sums, d_counts);
+    tg::k_bundle_final<<<(unsigned)B, tg::kFinalThreads, 0, st>>>(df, (const double*)c->d_tsum.p, (const int64_t*)c->d_tcnt.p, d_sums, d_counts);
     c->launches += 1;
     TG_CUDA(cudaGetLastError());
     return TG_OK;
