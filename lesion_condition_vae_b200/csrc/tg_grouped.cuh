@@ -112,6 +112,13 @@ __device__ __forceinline__ void st_keep(double* p, double v, uint64_t policy) {
     *p = v;
 #endif
 }
+// ticket counter: a plain atom.add in PTX — with atomicAdd() ptxas emits its warp-aggregation sequence, whose
+// leader broadcast (SHFL) waits for the atomic right where it was issued
+__device__ __forceinline__ unsigned long long take_ticket(unsigned long long* p) {
+    unsigned long long old;
+    asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(old) : "l"(p) : "memory");
+    return old;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
@@ -602,7 +609,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
     uint4 rec = make_uint4(0u, 0u, 0u, 0u);
     if (g < n_groups && (g << 5) + lane < M) rec = __ldg(queue + (g << 5) + lane);
     int64_t gn = 0;
-    if (lane == 0) gn = warps_total + (int64_t)atomicAdd(ticket, 1ull);
+    if (lane == 0) gn = warps_total + (int64_t)take_ticket(ticket);
     gn = __shfl_sync(0xffffffffu, gn, 0);
 
     while (g < n_groups) {
@@ -612,7 +619,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
         const int64_t s = (int64_t)rec.w;
         if (gn < n_groups && (gn << 5) + lane < M) rec = __ldg(queue + (gn << 5) + lane);   // used by the next iteration
         unsigned long long tk = 0ull;
-        if (lane == 0) tk = atomicAdd(ticket, 1ull);                                          // used at the end of this one
+        if (lane == 0) tk = take_ticket(ticket);                                          // used at the end of this one
         const double* base = xyz + 3 * o0;
         const uint64_t baddr = (uint64_t)(uintptr_t)base;
         const int skew = act ? (int)(baddr & 31u) : 0;                 // 0, 8, 16 or 24
@@ -772,7 +779,12 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
         }
         __syncwarp();
         g = gn;
-        gn = warps_total + (int64_t)__shfl_sync(0xffffffffu, tk, 0);
+        {   // broadcast the ticket only now: an opaque zero keeps the compiler from hoisting the shuffle up to the
+            // atomic (where its latency would be exposed); asm volatile stays behind the cp.async statements above
+            unsigned long long zero;
+            asm volatile("mov.u64 %0, 0;" : "=l"(zero));
+            gn = warps_total + (int64_t)__shfl_sync(0xffffffffu, tk + zero, 0);
+        }
     }
 }
 
