@@ -288,13 +288,14 @@ struct Sums {
 #else
     double mn0, mn1, mn2, mx0, mx1, mx2;
 #endif
-    double kK, k1, k2, en, ta;     // curvature shift / shifted moments, energy, torsion sum
+    double kK, k1, k2, en, ta;     // curvature shift / shifted moments, sum kappa_j^2 |d_j|, torsion sum
+    double kl;                     // kappa_{n-1}: the energy's eps * sum_{j<n-1} kappa_j^2 term comes from the moments
 };
 struct Pipe {
     double p1x, p1y, p1z, p2x, p2y, p2z;      // P(k-1), P(k-2)
     double tx, ty, tz, u_prev, len_prev;      // unit segment k-2, eps/|d_{k-2}|, |d_{k-2}|
     double vax, vay, vaz, vbx, vby, vbz;      // Vs_{k-2}, Vs_{k-3}       (Vs = 2 v)
-    double bax, bay, baz, bba, bbx, bby, bbz; // B_{k-3}, |B_{k-3}|^2, B_{k-4}   (B = 8 b)
+    double bax, bay, baz, bba, dprev;         // B_{k-3}, |B_{k-3}|^2, B_{k-4}.B_{k-3}   (B = 8 b)
 };
 
 __device__ __forceinline__ void sums_init(Sums& A) {
@@ -307,7 +308,7 @@ __device__ __forceinline__ void sums_init(Sums& A) {
     A.mn0 = A.mn1 = A.mn2 = __longlong_as_double(0x7ff0000000000000LL);
     A.mx0 = A.mx1 = A.mx2 = __longlong_as_double(0xfff0000000000000LL);
 #endif
-    A.kK = A.k1 = A.k2 = A.en = A.ta = 0.0;
+    A.kK = A.k1 = A.k2 = A.en = A.ta = A.kl = 0.0;
 }
 // double <-> signed 64-bit key with the same ordering (an involution: flip the low 63 bits of negatives)
 __device__ __forceinline__ long long order_key(double x) {
@@ -320,7 +321,7 @@ __device__ __forceinline__ void pipe_init(Pipe& S) {
     S.p1x = S.p1y = S.p1z = S.p2x = S.p2y = S.p2z = 0.0;
     S.tx = S.ty = S.tz = S.u_prev = S.len_prev = 0.0;
     S.vax = S.vay = S.vaz = S.vbx = S.vby = S.vbz = 0.0;
-    S.bax = S.bay = S.baz = S.bba = S.bbx = S.bby = S.bbz = 0.0;
+    S.bax = S.bay = S.baz = S.bba = S.dprev = 0.0;
 }
 
 constexpr int kHi_4em9 = 0x3E312DFE;    // high word of ~4e-9: |Vs|^2 above it <=> 2 eps/|Vs| < 3.3e-8 (second-order term < 1e-14)
@@ -468,8 +469,9 @@ __device__ __forceinline__ void lane_step(const int k, const int n, const double
         bad = max(bad, (MODE == MASKED && !pB) ? 0u : kchk);
         if (MODE != STEADY && k == 2) A.kK = kappa;                        // shift for the moments: kappa_0
         double dk = kappa - A.kK;
-        double kk = kappa * kappa;                                         // ref:77,82-83: kappa^2 (|d_j| + eps)
-        double ds = S.len_prev + kEps;
+        double kk = kappa * kappa;                                         // ref:77,82-83: kappa^2 (|d_j| + eps); the eps part is added in finalize
+        double ds = S.len_prev;
+        if (MODE != STEADY) A.kl = (k == n + 1) ? kappa : A.kl;
         if (MODE == MASKED) {
             dk = sel(pB, dk, 0.0);
             kk = sel(pE, kk, 0.0); ds = sel(pE, ds, 0.0);                  // 0*0: a masked-off lane may hold NaN in either
@@ -484,11 +486,14 @@ __device__ __forceinline__ void lane_step(const int k, const int n, const double
     }
 
     // ---- torsion stage j = k-3:  tau = b.db/(|b|^2 + eps) = s_j B_j.(B_{j+1} - B_{j-1}) / (|B_j|^2 + 64 eps)   (ref:91-95)
+    //      B_j.(B_{j+1} - B_{j-1}) = D_j - D_{j-1} with D_j = B_j.B_{j+1} (clamped ends: D_{-1} = |B_0|^2, D_{n-1} = |B_{n-1}|^2):
+    //      one new dot product per step; the rounding error it adds to tau is ~1e-16 ABSOLUTE (tau = num/|B|^2)
+    double dn = S.dprev;
     if (MODE != EDGE || pT) {
-        const double ex = bnx - S.bbx, ey = bny - S.bby, ez = bnz - S.bbz;
-        const double num = fma(S.baz, ez, fma(S.bay, ey, S.bax * ex));
+        dn = fma(S.baz, bnz, fma(S.bay, bny, S.bax * bnx));
+        const double num = dn - S.dprev;
         const double den = S.bba + 64.0 * kEps;
-        double rc = rcp_fast(den);                                         // den in [6.4e-11, 1e300) whenever ok
+        double rc = rcp_fast(den);                                         // den in [6.4e-11, 1e300) whenever the lane is valid
         const bool end = MODE != STEADY && (k == 3 || k == n + 2);         // s = 1 at the ends, 1/2 inside
         rc = end ? rc : scale_pow2_down(rc, 1);
         const double tau = num * rc;
@@ -497,12 +502,12 @@ __device__ __forceinline__ void lane_step(const int k, const int n, const double
 
     // ---- rotate (left clamp F(-1) := F(0) for the two gradient levels)
     if (MODE != STEADY) {
-        const bool c1 = (k == 1), c2 = (k == 2);
+        const bool c1 = (k == 1);
         S.vbx = sel(c1, vnx, S.vax); S.vby = sel(c1, vny, S.vay); S.vbz = sel(c1, vnz, S.vaz);
-        S.bbx = sel(c2, bnx, S.bax); S.bby = sel(c2, bny, S.bay); S.bbz = sel(c2, bnz, S.baz);
+        S.dprev = (k == 2) ? bbn : dn;                                     // D_{-1} = B_0.B_0
     } else {
         S.vbx = S.vax; S.vby = S.vay; S.vbz = S.vaz;
-        S.bbx = S.bax; S.bby = S.bay; S.bbz = S.baz;
+        S.dprev = dn;
     }
     S.vax = vnx; S.vay = vny; S.vaz = vnz;
     S.bax = bnx; S.bay = bny; S.baz = bnz; S.bba = bbn;
@@ -551,9 +556,12 @@ __device__ __forceinline__ unsigned finalize_grouped(const Sums& A, const int n,
         double m2c = A.k2 - A.k1 * dm;
         st_keep(out + 4 * S + s, A.kK + dm, pol);
         st_keep(out + 5 * S + s, sqrt(fmax(m2c, 0.0) * rn), pol);
+        // ref:82-83: sum_{j<n-1} kappa_j^2 (|d_j| + eps) = A.en + eps (sum_all kappa^2 - kappa_{n-1}^2), with
+        // sum_all kappa^2 = k2 + 2 K k1 + n K^2 from the shifted moments (a 1e-12-relative term: any rounding is fine)
+        const double sk2 = fma(A.kK, fma(dn, A.kK, 2.0 * A.k1), A.k2) - A.kl * A.kl;
+        st_keep(out + 6 * S + s, fma(kEps, sk2, A.en), pol);
     }
-    st_keep(out + 6 * S + s, A.en, pol);
-    st_keep(out + 7 * S + s, (n >= 4) ? A.ta * rn : 0.0, pol);                           // ref:86-87,96
+        st_keep(out + 7 * S + s, (n >= 4) ? A.ta * rn : 0.0, pol);                           // ref:86-87,96
     st_keep(out + 8 * S + s, A.th / (double)(n - 2), pol);                               // ref:106
     st_keep(out + 9 * S + s, ((key_value(A.mx0) - key_value(A.mn0)) * (key_value(A.mx1) - key_value(A.mn1))) * (key_value(A.mx2) - key_value(A.mn2)), pol);   // ref:117
     double g0 = A.q0 * rn, g1 = A.q1 * rn, g2 = A.q2 * rn;                 // centroid - m
