@@ -22,7 +22,7 @@
 //
 // fp64-pipe budget: the B200 issues ~60 fp64 lane-operations / SM / clock (tools/microbench.cu),
 // and at 25.45 algorithmic bytes per point that roof sits BELOW the HBM roof for this metric set,
-// so the arithmetic is organised to need 97 fp64-pipe instructions per interior point (v1: ~145):
+// so the arithmetic is organised to need 95 fp64-pipe instructions per interior point (v1: ~145):
 //   - every power-of-two scale factor of np.gradient is folded out: the pipeline carries
 //     Vs = 2 v and B = 8 b (exact scalings), so the interior needs no multiplications by 1/2;
 //   - kappa = |B| / (|Vs| + 2e-12)^3 comes from ONE rsqrt of |Vs|^6 |B|^2; the additive epsilon is
@@ -33,7 +33,7 @@
 //   - the finite test of the loader filter rides on the centroid sums (a non-finite coordinate
 //     makes them non-finite).
 // The streaming step is SPECULATIVE: it assumes well-conditioned geometry (segments and
-// velocities of ordinary magnitude, non-collinear triples, turning angle < 29 degrees) and keeps
+// velocities of ordinary magnitude, non-collinear triples, turning angle < 60 degrees) and keeps
 // a sticky per-lane `ok` flag; a polyline whose flag drops is recomputed by the exact general
 // pipeline of tg_device.cuh (stream_chunk) by its lane after the group has finished.
 // Three instantiations of the step share the same arithmetic, operation for operation (the
@@ -129,15 +129,16 @@ __device__ __forceinline__ double scale_pow2_down(double x, int k) {
 }
 __device__ __forceinline__ double sel(bool p, double a, double b) { return p ? a : b; }
 
-// tail of asin(s)/s - 1 - z/6, z = s^2 <= 1/16, in fp32 (|tail| <= 3e-4, so fp32 leaves < 4e-11)
+// tail of asin(s)/s - 1 - z/6 - 3 z^2/40, z = s^2 <= 1/4 (turning angle <= 60 degrees), in fp32: z^3 R(z) with a
+// degree-5 minimax R; |tail| <= 8.4e-4 and the fp32 evaluation is within 1.3e-10 of it over the whole range
 __device__ __forceinline__ float asin_tail_f32(float z) {
-    float r = 0.01396484f;
-    r = fmaf(r, z, 0.017352764f);
-    r = fmaf(r, z, 0.022372159f);
-    r = fmaf(r, z, 0.030381944f);
-    r = fmaf(r, z, 0.044642857f);
-    r = fmaf(r, z, 0.075f);
-    return r * (z * z);
+    float r = 0.023272162f;
+    r = fmaf(r, z, 0.010175252f);
+    r = fmaf(r, z, 0.017879551f);
+    r = fmaf(r, z, 0.022339951f);
+    r = fmaf(r, z, 0.030382656f);
+    r = fmaf(r, z, 0.044642854f);
+    return r * (z * z * z);
 }
 
 // ==========================================================================================
@@ -326,7 +327,7 @@ __device__ __forceinline__ void pipe_init(Pipe& S) {
 
 constexpr int kHi_4em9 = 0x3E312DFE;    // high word of ~4e-9: |Vs|^2 above it <=> 2 eps/|Vs| < 3.3e-8 (second-order term < 1e-14)
 constexpr int kHi_1em8 = 0x3E45798F;    // high word of ~1e-8: |d|^2 above it <=> eps/|d| < 1e-8
-constexpr int kHi_quarter = 0x3FD00000; // high word of 0.25
+constexpr int kHi_one = 0x3FF00000;     // high word of 1.0
 // Validity of the speculative path is tracked as ONE unsigned maximum per lane (a VIADDMNMX per test):
 // test i contributes hi(x) - lo_i; the lane is fine iff the maximum stays below kChkSpan.  A value below
 // its lower limit wraps to ~2^32; the common span makes the upper limits lo_i * 2^1023 (>= 9e27).
@@ -356,13 +357,13 @@ __device__ __forceinline__ double angle_math(const SegOut& s, const double tx, c
     const double ex = s.ux - tx, ey = s.uy - ty, ez = s.uz - tz;
     const double dd = fma(ez, ez, fma(ey, ey, ex * ex));
     const double Z = fma(2.0, s.u + u_prev, dd);     // 4 sin^2(theta/2)
-    chk = chk_below(Z, kHi_quarter);
+    chk = chk_below(Z, kHi_one);                     // Z = 4 sin^2(theta/2) < 1: turning angle < 60 degrees
     const double yz = mufu_rsqrt(Z);                 // quadratic step: 1.3e-12 relative on theta
     const double tz_ = Z * yz;
     const double ez_ = fma(-tz_, yz, 1.0);
     const double sZ = fma(scale_pow2_down(tz_, 1), ez_, tz_);      // sqrt(Z) = 2 sin(theta/2)
     const float zf = 0.25f * __double2float_rn(Z);
-    const double w = fma(Z, 1.0 / 24.0, (double)asin_tail_f32(zf));
+    const double w = fma(Z, fma(Z, 3.0 / 640.0, 1.0 / 24.0), (double)asin_tail_f32(zf));   // z/6 + 3 z^2/40 + tail, z = Z/4
     return fma(sZ, w, sZ);
 }
 // kappa_j = |b_j| / (|v_j| + eps)^3 = |B_j| / (|Vs_j| + 2 eps)^3 = |B|^2 rsqrt(|Vs|^6 |B|^2) (1 - 6 eps/|Vs| + ...)   ref:57-59

@@ -80,6 +80,18 @@ def test_random_tracts_vs_oracle(gpu_ctx, seed, law):
     assert_bundle_close(df_b.iloc[0].to_numpy(float), ref_b.iloc[0].to_numpy(float), ref_sl.to_numpy(), law)
 
 
+@pytest.mark.parametrize("sigma", [0.2, 0.45, 0.9])
+def test_sharp_turns(gpu_ctx, sigma):
+    """Turning angles around and beyond the 60-degree limit of the speculative angle series: polylines
+    below it stay on the fast path (series + fp32 tail), the others are recomputed exactly; both must
+    match the oracle."""
+    rng = np.random.default_rng(51)
+    pts, off = synth.random_walk_csr(synth.lengths_uniform(rng, 400, 5, 90), 51, sigma=sigma)
+    df_sl, _ = tgp.compute_streamline_metrics_csr(pts, off, ctx=gpu_ctx)
+    ref_sl, _ = so.compute_streamline_metrics_csr(pts, off)
+    assert_table_close(df_sl.to_numpy(), ref_sl.to_numpy(), f"sigma={sigma}")
+
+
 def test_far_from_origin_covariance(gpu_ctx):
     """a one-pass raw-coordinate covariance fails at +1000 mm; ours must not."""
     rng = np.random.default_rng(31)
