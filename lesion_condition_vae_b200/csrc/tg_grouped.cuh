@@ -547,32 +547,32 @@ __device__ __forceinline__ unsigned finalize_grouped(const Sums& A, const int n,
     const double rn = rcp_fast(dn), rn1 = rcp_fast(dn - 1.0);             // 1/n, 1/(n-1) to 2^-58
     const double L = A.L;                                                  // > 1e-4 (n-1) on this path: ref:160 passes
     double cx = e0 - f0, cy = e1 - f1, cz = e2 - f2;
-    double chord = sqrt(cx * cx + cy * cy + cz * cz);                      // ref:36
+    double chord = sqrt_fast(cx * cx + cy * cy + cz * cz);                 // ref:36 (divisions below: x * rcp_fast(y), 2^-58 relative)
     st_keep(out + 0 * S + s, L, pol);
     st_keep(out + 1 * S + s, chord, pol);
-    st_keep(out + 2 * S + s, L / fmax(chord, kMinLen), pol);                             // ref:38-41
-    st_keep(out + 3 * S + s, chord / fmax(L, kMinLen), pol);                             // ref:43-46
+    st_keep(out + 2 * S + s, L * rcp_fast(fmax(chord, kMinLen)), pol);                             // ref:38-41
+    st_keep(out + 3 * S + s, chord * rcp_fast(fmax(L, kMinLen)), pol);                             // ref:43-46
     {                                                                      // ref:61,71: all n curvatures are finite here
         double dm = A.k1 * rn;
         double m2c = A.k2 - A.k1 * dm;
         st_keep(out + 4 * S + s, A.kK + dm, pol);
-        st_keep(out + 5 * S + s, sqrt(fmax(m2c, 0.0) * rn), pol);
+        st_keep(out + 5 * S + s, sqrt_fast(fmax(m2c, 0.0) * rn), pol);
         // ref:82-83: sum_{j<n-1} kappa_j^2 (|d_j| + eps) = A.en + eps (sum_all kappa^2 - kappa_{n-1}^2), with
         // sum_all kappa^2 = k2 + 2 K k1 + n K^2 from the shifted moments (a 1e-12-relative term: any rounding is fine)
         const double sk2 = fma(A.kK, fma(dn, A.kK, 2.0 * A.k1), A.k2) - A.kl * A.kl;
         st_keep(out + 6 * S + s, fma(kEps, sk2, A.en), pol);
     }
         st_keep(out + 7 * S + s, (n >= 4) ? A.ta * rn : 0.0, pol);                           // ref:86-87,96
-    st_keep(out + 8 * S + s, A.th / (double)(n - 2), pol);                               // ref:106
+    st_keep(out + 8 * S + s, A.th * rcp_fast((double)(n - 2)), pol);                               // ref:106
     st_keep(out + 9 * S + s, ((key_value(A.mx0) - key_value(A.mn0)) * (key_value(A.mx1) - key_value(A.mn1))) * (key_value(A.mx2) - key_value(A.mn2)), pol);   // ref:117
     double g0 = A.q0 * rn, g1 = A.q1 * rn, g2 = A.q2 * rn;                 // centroid - m
     double c00 = fma(-A.q0, g0, A.q00) * rn1, c01 = fma(-A.q0, g1, A.q01) * rn1, c02 = fma(-A.q0, g2, A.q02) * rn1;
     double c11 = fma(-A.q1, g1, A.q11) * rn1, c12 = fma(-A.q1, g2, A.q12) * rn1, c22 = fma(-A.q2, g2, A.q22) * rn1;
     double l1, l2, l3;
     sym3_eigenvalues(c00, c01, c02, c11, c12, c22, l1, l2, l3);
-    st_keep(out + 10 * S + s, (l2 <= kEps) ? inf : l1 / l2, pol);                        // ref:126-130
-    st_keep(out + 11 * S + s, (l3 <= kEps) ? inf : l2 / l3, pol);                        // ref:132-136
-    st_keep(out + 12 * S + s, l1 / (((l1 + l2) + l3) + kEps), pol);                      // ref:138-141
+    st_keep(out + 10 * S + s, (l2 <= kEps) ? inf : l1 * rcp_fast(l2), pol);                        // ref:126-130
+    st_keep(out + 11 * S + s, (l3 <= kEps) ? inf : l2 * rcp_fast(l3), pol);                        // ref:132-136
+    st_keep(out + 12 * S + s, l1 * rcp_fast(((l1 + l2) + l3) + kEps), pol);                      // ref:138-141
     st_keep(out + 13 * S + s, m0 + g0, pol);                                             // ref:183-185
     st_keep(out + 14 * S + s, m1 + g1, pol);
     st_keep(out + 15 * S + s, m2 + g2, pol);
