@@ -67,11 +67,11 @@ constexpr int kChunk = TG_CHUNK;              // points per ring slot (even, mul
 constexpr int kSub = TG_SUB;                  // steps per unrolled sub-block (3 = rotation period of the pipeline registers)
 constexpr int kHead = ((6 + kSub - 1) / kSub) * kSub;   // first steps of a polyline, run as specialised EDGE steps (>= 4 needed)
 static_assert(kChunk % kSub == 0 && kChunk % 2 == 0 && kHead <= kChunk, "chunk / sub-block geometry");
-static_assert(kChunk == 12, "stage_chunk issues exactly 2-3 pieces per lane: 18/20 pieces per slot");
 constexpr int kChunkBytes = kChunk * 24;      // 288
 constexpr int kSlotBytes = kChunkBytes + 32;  // one 32-byte sector of lead-out: a point never straddles two slots
 constexpr int kRingStride = 2 * kSlotBytes + 16;   // 656 B per lane: 16-B aligned, 2-way bank conflicts at worst
 constexpr int kPieces = kSlotBytes / 16;      // 20 cp.async pieces per slot
+static_assert(kPieces <= 24, "stage_chunk issues at most 3 pieces per lane and polyline");
 constexpr int kWarpSmem = 32 * kRingStride + 32 * 16;   // ring + stream descriptors
 constexpr int kGroupedSmem = kWarpsPerCta * kWarpSmem;
 
@@ -667,15 +667,16 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
             const int skip = q > 0 ? 32 : 0;
             const int pos0 = q * kChunkBytes + skip + part * 16;       // byte position in the aligned stream
             const uint32_t dst0 = stage_dst0 + (q & 1) * kSlotBytes + skip;
-            const bool third = part < (q > 0 ? kPieces - 18 : kPieces - 16);
+            const int pieces = q > 0 ? kChunkBytes / 16 : kPieces;     // 16-byte pieces of this slot that come from memory
+            const bool second = part + 8 < pieces, third = part + 16 < pieces;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const unsigned char* src = (const unsigned char*)(uintptr_t)sd_src[i] + pos0;
                 const int rem = sd_len[i] - pos0;
                 const uint32_t dst = dst0 + i * (4 * kRingStride);
                 cp_async16_if<0, 0>(dst, src, rem, l2_stream);
-                cp_async16_if<128, 128>(dst, src, rem, l2_stream);
-                if (third) cp_async16_if<256, 256>(dst, src, rem, l2_stream);
+                if (kPieces > 16 || second) cp_async16_if<128, 128>(dst, src, rem, l2_stream);
+                if (kPieces > 16 && third) cp_async16_if<256, 256>(dst, src, rem, l2_stream);
             }
             cp_async_commit();
         };
