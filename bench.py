@@ -46,7 +46,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streamlines", type=int, default=int(os.environ.get("TG_BENCH_STREAMLINES", 10_000_000)),
                     help="polylines per GPU (default: 10M = BASELINE config 5 on one GPU)")
-    ap.add_argument("--law", default="normal", choices=["normal", "heavy"], help="length law (heavy = config 4)")
+    ap.add_argument("--law", default="normal", choices=["normal", "heavy", "fixed96"], help="length law (heavy = config 4; fixed96 = traffic probe)")
     ap.add_argument("--e2e-streamlines", type=int, default=int(os.environ.get("TG_BENCH_E2E_STREAMLINES", 1_000_000)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("TG_BENCH_CPU_SAMPLE", 100_000)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -205,7 +205,7 @@ def run_ours(args):
     ctx = _lib.Context(local)
     S = args.streamlines
     seed = 5 + 1000 * rank
-    n = synth.torch_lengths("normal" if args.law == "normal" else "heavy", S, seed, dev)
+    n = synth.torch_lengths(args.law, S, seed, dev)
     pts, off = synth.torch_random_walk_csr(n, seed, dev)
     P = int(pts.shape[0])
     del n

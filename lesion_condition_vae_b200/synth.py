@@ -165,6 +165,8 @@ def torch_lengths(kind, S, seed, device):
         return torch.clamp(torch.floor(10.0 / u), max=5000.0).to(torch.int64)
     if kind == "uniform":
         return torch.randint(20, 120, (S,), generator=g, device=device, dtype=torch.int64)
+    if kind == "fixed96":                      # every polyline 96 points = 36 whole 64-byte atoms (traffic probe)
+        return torch.full((S,), 96, device=device, dtype=torch.int64)
     raise ValueError(kind)
 
 
