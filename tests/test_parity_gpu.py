@@ -260,3 +260,49 @@ def test_heavy_tail_at_scale_subsample(gpu_ctx):
     off_h = off.cpu().numpy()
     rows = [so.metrics_row(pts[off_h[s]:off_h[s + 1]].cpu().numpy()) for s in idx]
     assert_table_close(out[:, torch.as_tensor(idx, device=dev)].T.cpu().numpy(), np.asarray(rows), "heavy subsample")
+
+
+def test_degenerate_grid_polylines(gpu_ctx):
+    """Integer-grid polylines (duplicate points, collinear triples, right angles, reversals): almost every
+    one leaves the speculative path and is recomputed by the exact pipeline; inf / NaN-to-number / zero
+    semantics of the reference (ref:60, 81, 95, 128, 134) must come out the same."""
+    import warnings
+    rng = np.random.default_rng(2024)
+    lines = [rng.integers(-2, 3, size=(int(rng.integers(3, 13)), 3)).astype(np.float64) for _ in range(400)]
+    pts, off = synth.lines_to_csr(lines)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_sl, ref_b = so.compute_streamline_metrics_csr(pts, off)
+    df_sl, df_b = tgp.compute_streamline_metrics_csr(pts, off, ctx=gpu_ctx)
+    assert len(df_sl) == len(ref_sl)
+    assert_table_close(df_sl.to_numpy(), ref_sl.to_numpy(), "grid")
+
+
+@pytest.mark.parametrize("scale", [1e-6, 1e-3, 1e3, 1e6])
+def test_coordinate_units(gpu_ctx, scale):
+    """The additive 1e-12 / 1e-8 epsilons of the reference make the metrics unit-dependent; the speculative
+    path has to notice when its first-order treatment of them stops being valid (tiny units) and hand
+    over to the exact pipeline.  Same tractogram in micrometres ... kilometres-ish."""
+    import warnings
+    rng = np.random.default_rng(61)
+    pts, off = synth.random_walk_csr(synth.lengths_uniform(rng, 300, 3, 80), 61)
+    pts = pts * scale
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_sl, _ = so.compute_streamline_metrics_csr(pts, off)
+    df_sl, _ = tgp.compute_streamline_metrics_csr(pts, off, ctx=gpu_ctx)
+    assert len(df_sl) == len(ref_sl)
+    got, ref = df_sl.to_numpy(), ref_sl.to_numpy()
+    # absolute floors of parity_rules.py are written for millimetre data: scale them with the unit of each column
+    from parity_rules import ATOL, COLUMNS, column_errors
+    unit = {"length": 1, "end_to_end": 1, "curv_mean": -1, "curv_std": -1, "curv_energy": -1, "bbox_vol": 3,
+            "centroid_x": 1, "centroid_y": 1, "centroid_z": 1}
+    saved = dict(ATOL)
+    try:
+        for k, p in unit.items():
+            ATOL[k] = saved[k] * max(scale ** p, 1.0)
+        errs = column_errors(got, ref)
+    finally:
+        ATOL.update(saved)
+    bad = {k: v for k, v in errs.items() if not v <= 1.0}
+    assert not bad, (scale, bad)
