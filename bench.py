@@ -46,7 +46,8 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streamlines", type=int, default=int(os.environ.get("TG_BENCH_STREAMLINES", 10_000_000)),
                     help="polylines per GPU (default: 10M = BASELINE config 5 on one GPU)")
-    ap.add_argument("--law", default="normal", choices=["normal", "heavy", "fixed96"], help="length law (heavy = config 4; fixed96 = traffic probe)")
+    ap.add_argument("--law", default="normal", choices=["normal", "heavy", "loguniform", "fixed96"],
+                    help="length law (heavy = config 4; loguniform = its long-polyline variant; fixed96 = traffic probe)")
     ap.add_argument("--e2e-streamlines", type=int, default=int(os.environ.get("TG_BENCH_E2E_STREAMLINES", 1_000_000)))
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("TG_BENCH_CPU_SAMPLE", 100_000)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -57,6 +58,8 @@ def parse_args():
 def workload_name(S, law):
     if law == "normal":
         return f"synthetic tractogram, {S} polylines/GPU x ~100 points (n=clip(round(N(100,15^2)),3,200)), float64 CSR (BASELINE configs[4])"
+    if law == "loguniform":
+        return f"log-uniform tractogram, {S} polylines/GPU, n=floor(10*500^U) in [10,5000], mean ~803 (variant of BASELINE configs[3])"
     return f"heavy-tailed tractogram, {S} polylines/GPU, n=min(5000,floor(10/U)) (BASELINE configs[3])"
 
 
@@ -135,7 +138,12 @@ def host_sample(S, law, seed=5):
     import numpy as np
     from lesion_condition_vae_b200 import synth
     rng = np.random.default_rng(seed)
-    n = synth.lengths_normal(rng, S, CFG_MEAN, CFG_SD, CFG_LO, CFG_HI) if law == "normal" else synth.lengths_heavy_tail(rng, S)
+    if law == "normal":
+        n = synth.lengths_normal(rng, S, CFG_MEAN, CFG_SD, CFG_LO, CFG_HI)
+    elif law == "loguniform":
+        n = synth.lengths_log_uniform(rng, S)
+    else:
+        n = synth.lengths_heavy_tail(rng, S)
     return synth.random_walk_csr(n, seed)
 
 

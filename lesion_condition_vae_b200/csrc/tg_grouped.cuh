@@ -3,10 +3,13 @@
 //
 // Work decomposition:
 //   * QUEUE.  A device-side counting sort orders the polylines of every window of kWindow
-//     consecutive polylines by point count (bins 3..kMaxGroupedN; shorter ones get their NaN row
-//     at once, longer ones are flagged for the long-polyline kernel).  Cutting that order into
-//     consecutive GROUPS of 32 gives groups whose members have the same length (a few per cent
-//     straddle a bin boundary).
+//     consecutive polylines by point count (one bin per length, 3..kShortMax; shorter ones get their
+//     NaN row at once).  Cutting that order into consecutive GROUPS of 32 gives groups whose members
+//     have the same length (a few per cent straddle a bin boundary).  Polylines of up to
+//     kMaxGroupedN points form one extra row at the head of the queue, longest first (so the longest
+//     groups start first and never form the tail of the launch) — when there are enough of them to
+//     fill the machine; otherwise, and beyond kMaxGroupedN, they are flagged for the one-warp-per-
+//     polyline kernel.
 //   * STREAM.  A persistent grid of one 8-warp CTA per SM; every warp is an independent worker
 //     that takes groups round-robin, one polyline per lane, so all 32 lanes run the same number
 //     of iterations — no ragged-length divergence, no halo recomputation, no shuffles.
@@ -75,8 +78,17 @@ static_assert(kPieces <= 24, "stage_chunk issues at most 3 pieces per lane and p
 constexpr int kWarpSmem = 32 * kRingStride + 32 * 16;   // ring + stream descriptors
 constexpr int kGroupedSmem = kWarpsPerCta * kWarpSmem;
 
-constexpr int kBins = 2048;                   // length bins of the queue
-constexpr int kMaxGroupedN = kBins - 2;       // polylines with more points take the long-polyline kernel
+constexpr int kBins = 2048;                   // bins per queue row
+// Queue rows.  Rows 1 .. n_windows: one per window of kWindow consecutive polylines, polylines of 3 .. kShortMax
+// points, one bin per length, ascending.  Row 0 (first in the queue, so its groups start first): the polylines
+// of kShortMax+1 .. kMaxGroupedN points of the WHOLE table, 4 lengths per bin, longest first — used when there
+// are at least kLongGroupedMin of them (enough groups to keep the SMs busy); otherwise, and beyond
+// kMaxGroupedN, a polyline goes to the one-warp-per-polyline kernel.
+constexpr int kShortMax = 1024;
+constexpr int kLongShift = 2;
+constexpr int kMaxGroupedN = kShortMax + (kBins << kLongShift);
+constexpr int kLongGroupedMin = 6144;
+__device__ __forceinline__ int long_bin(const int64_t n) { return kBins - 1 - (int)((n - (kShortMax + 1)) >> kLongShift); }
 #ifndef TG_WINDOW_LOG2
 #define TG_WINDOW_LOG2 17
 #endif
@@ -144,25 +156,29 @@ __device__ __forceinline__ float asin_tail_f32(float z) {
 // ==========================================================================================
 // Queue kernels
 // ==========================================================================================
-// hist[w * kBins + n]: polylines of window w with n points (3 <= n <= kMaxGroupedN)
+// hist[(1 + w) * kBins + n]: polylines of window w with n points (3 <= n <= kShortMax);
+// hist[long_bin(n)]: polylines of the whole table with kShortMax < n <= kMaxGroupedN points
 __global__ void __launch_bounds__(kBinThreads)
 k_bin_count(const int64_t* __restrict__ offsets, const int64_t S, unsigned* __restrict__ hist) {
-    __shared__ unsigned sh[kBins];
-    for (int i = threadIdx.x; i < kBins; i += kBinThreads) sh[i] = 0u;
+    __shared__ unsigned sh[2 * kBins];       // [0, kBins): this window's row, [kBins, 2 kBins): row 0
+    for (int i = threadIdx.x; i < 2 * kBins; i += kBinThreads) sh[i] = 0u;
     __syncthreads();
     const int64_t s0 = (int64_t)blockIdx.x * kBinSeg;
     const int64_t s1 = min(s0 + kBinSeg, S);
     for (int64_t s = s0 + threadIdx.x; s < s1; s += kBinThreads) {
         const int64_t n = __ldg(offsets + s + 1) - __ldg(offsets + s);
-        if (n >= 3 && n <= kMaxGroupedN) atomicAdd(&sh[(int)n], 1u);
+        if (n >= 3 && n <= kShortMax) atomicAdd(&sh[(int)n], 1u);
+        else if (n > kShortMax && n <= kMaxGroupedN) atomicAdd(&sh[kBins + long_bin(n)], 1u);
     }
     __syncthreads();
-    unsigned* h = hist + (s0 >> kWindowLog2) * kBins;
-    for (int i = threadIdx.x; i < kBins; i += kBinThreads)
+    unsigned* h = hist + (1 + (s0 >> kWindowLog2)) * kBins;
+    for (int i = threadIdx.x; i < kBins; i += kBinThreads) {
         if (sh[i] != 0u) atomicAdd(&h[i], sh[i]);
+        if (sh[kBins + i] != 0u) atomicAdd(&hist[i], sh[kBins + i]);
+    }
 }
 
-// hist[w] -> exclusive start positions inside window w (one CTA per window); wtotal[w] = polylines queued from window w.
+// hist[r] -> exclusive start positions inside row r (one CTA per row); wtotal[r] = polylines queued in row r.
 // hist becomes the scatter cursor (zeroed).
 __global__ void __launch_bounds__(1024)
 k_bin_scan(unsigned* __restrict__ hist, int64_t* __restrict__ start, int64_t* __restrict__ wtotal) {
@@ -197,13 +213,19 @@ k_bin_scan(unsigned* __restrict__ hist, int64_t* __restrict__ start, int64_t* __
     if (threadIdx.x == 0) wtotal[w] = (int64_t)wsum[31];
 }
 
-// wtotal -> exclusive window bases (in place); total[0] = queue length M.  One CTA; windows are few.
+// wtotal -> exclusive row bases (in place); total[0] = queue length M.  One CTA; rows are few.
+// Decides whether row 0 is worth queueing (long_grouped[0] = 1) or its polylines go to k_metrics_long.
 __global__ void __launch_bounds__(1024)
-k_window_scan(int64_t* __restrict__ wtotal, const int64_t n_windows, int64_t* __restrict__ total) {
+k_window_scan(int64_t* __restrict__ wtotal, const int64_t n_windows, int64_t* __restrict__ total, int* __restrict__ long_grouped) {
     __shared__ int64_t wsum[32];
     __shared__ int64_t run;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (threadIdx.x == 0) run = 0;
+    if (threadIdx.x == 0) {
+        run = 0;
+        const bool grouped = wtotal[0] >= kLongGroupedMin;
+        long_grouped[0] = grouped ? 1 : 0;
+        if (!grouped) wtotal[0] = 0;
+    }
     __syncthreads();
     for (int64_t w0 = 0; w0 < n_windows; w0 += 1024) {
         const int64_t w = w0 + threadIdx.x;
@@ -234,42 +256,51 @@ k_window_scan(int64_t* __restrict__ wtotal, const int64_t n_windows, int64_t* __
     if (threadIdx.x == 0) total[0] = run;
 }
 
-// queue[start + rank] = {offset lo, offset hi, n, polyline id}; polylines with n < 3 get their NaN row
-// (ref:21); ids of polylines longer than kMaxGroupedN are appended, downwards, at the END of the
+// queue[row base + bin start + rank] = {offset lo, offset hi, n, polyline id}; polylines with n < 3 get their NaN
+// row (ref:21); ids of the polylines left to k_metrics_long are appended, downwards, at the END of the
 // queue buffer (records + ids never exceed its S x 16 bytes) and counted in n_long.
 __global__ void __launch_bounds__(kBinThreads)
 k_bin_scatter(const int64_t* __restrict__ offsets, const int64_t S, unsigned* __restrict__ cursor,
               const int64_t* __restrict__ start, const int64_t* __restrict__ wbase, uint4* __restrict__ queue, double* __restrict__ out,
-              const int64_t ld, uint8_t* __restrict__ keep, int* __restrict__ n_long) {
-    __shared__ unsigned sh[kBins];       // pass 1: count; then: next free rank inside this CTA's reservation
-    for (int i = threadIdx.x; i < kBins; i += kBinThreads) sh[i] = 0u;
+              const int64_t ld, uint8_t* __restrict__ keep, int* __restrict__ n_long, const int* __restrict__ long_grouped) {
+    __shared__ unsigned sh[2 * kBins];   // pass 1: count; then: next free rank inside this CTA's reservation
+    for (int i = threadIdx.x; i < 2 * kBins; i += kBinThreads) sh[i] = 0u;
     __syncthreads();
     const int64_t s0 = (int64_t)blockIdx.x * kBinSeg;
     const int64_t s1 = min(s0 + kBinSeg, S);
-    const int64_t w = s0 >> kWindowLog2;
+    const int64_t row = 1 + (s0 >> kWindowLog2);
+    const int64_t max_row0 = long_grouped[0] ? kMaxGroupedN : kShortMax;   // longest polyline that is queued
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     unsigned* long_end = (unsigned*)(queue + S);
     for (int64_t s = s0 + threadIdx.x; s < s1; s += kBinThreads) {
         const int64_t n = __ldg(offsets + s + 1) - __ldg(offsets + s);
-        if (n >= 3 && n <= kMaxGroupedN) atomicAdd(&sh[(int)n], 1u);
+        if (n >= 3 && n <= kShortMax) atomicAdd(&sh[(int)n], 1u);
         else if (n < 3) {
 #pragma unroll
             for (int m = 0; m < 17; ++m) out[(int64_t)m * ld + s] = nan;
             keep[s] = 0;
-        } else long_end[-1 - (int64_t)atomicAdd(n_long, 1)] = (unsigned)s;
+        } else if (n <= max_row0) atomicAdd(&sh[kBins + long_bin(n)], 1u);
+        else long_end[-1 - (int64_t)atomicAdd(n_long, 1)] = (unsigned)s;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < kBins; i += kBinThreads) {
         const unsigned c = sh[i];
-        if (c != 0u) sh[i] = atomicAdd(&cursor[w * kBins + i], c);     // reserve [r, r+c) in the bin
+        if (c != 0u) sh[i] = atomicAdd(&cursor[row * kBins + i], c);     // reserve [r, r+c) in the bin
+        const unsigned c0 = sh[kBins + i];
+        if (c0 != 0u) sh[kBins + i] = atomicAdd(&cursor[i], c0);
     }
     __syncthreads();
     for (int64_t s = s0 + threadIdx.x; s < s1; s += kBinThreads) {
         const int64_t o0 = __ldg(offsets + s);
         const int64_t n = __ldg(offsets + s + 1) - o0;
-        if (n >= 3 && n <= kMaxGroupedN) {
+        const uint4 record = make_uint4((unsigned)o0, (unsigned)((uint64_t)o0 >> 32), (unsigned)n, (unsigned)s);
+        if (n >= 3 && n <= kShortMax) {
             const unsigned r = atomicAdd(&sh[(int)n], 1u);
-            queue[wbase[w] + start[w * kBins + n] + r] = make_uint4((unsigned)o0, (unsigned)((uint64_t)o0 >> 32), (unsigned)n, (unsigned)s);
+            queue[wbase[row] + start[row * kBins + n] + r] = record;
+        } else if (n > kShortMax && n <= max_row0) {
+            const int b = long_bin(n);
+            const unsigned r = atomicAdd(&sh[kBins + b], 1u);
+            queue[wbase[0] + start[b] + r] = record;
         }
     }
 }

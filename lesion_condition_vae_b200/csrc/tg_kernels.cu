@@ -400,8 +400,8 @@ static int launch_metrics_f64(tg_context* c, const double* xyz, uint64_t lo, uin
         TG_CUDA(cudaFuncSetAttribute(tg::k_metrics_grouped, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::kGroupedSmem));
         c->grouped_ready = true;
     }
-    // queue scratch: [n_long | total | ticket], hist/cursor, start, queue records (+ long ids at the end)
-    const int64_t n_windows = (S + tg::kWindow - 1) / tg::kWindow;
+    // queue scratch: [n_long | total | ticket | long_grouped], hist/cursor, start, queue records (+ long ids at the end)
+    const int64_t n_windows = (S + tg::kWindow - 1) / tg::kWindow + 1;   // queue rows: row 0 (long polylines) + one per window
     int rc;
     if (!c->d_qhead.p) {
         if ((rc = c->d_qhead.reserve(64))) return rc;
@@ -413,17 +413,18 @@ static int launch_metrics_f64(tg_context* c, const double* xyz, uint64_t lo, uin
     int* d_nlong = (int*)c->d_qhead.p;
     int64_t* d_total = (int64_t*)((char*)c->d_qhead.p + 8);
     unsigned long long* d_ticket = (unsigned long long*)((char*)c->d_qhead.p + 16);
+    int* d_long_grouped = (int*)((char*)c->d_qhead.p + 24);
     unsigned* d_hist = (unsigned*)c->d_hist.p;
     int64_t* d_start = (int64_t*)c->d_start.p;
     int64_t* d_wbase = d_start + tg::kBins * n_windows;          // per-window totals, then bases
     uint4* d_queue = (uint4*)c->d_perm.p;
-    TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 32, st));          // n_long, total, ticket (the pipeline error word at +32 is sticky)
+    TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 32, st));          // n_long, total, ticket, long_grouped (the pipeline error word at +32 is sticky)
     TG_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * tg::kBins * (size_t)n_windows, st));
     const unsigned seg_grid = (unsigned)((S + tg::kBinSeg - 1) / tg::kBinSeg);
     tg::k_bin_count<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist);
     tg::k_bin_scan<<<(unsigned)n_windows, 1024, 0, st>>>(d_hist, d_start, d_wbase);
-    tg::k_window_scan<<<1, 1024, 0, st>>>(d_wbase, n_windows, d_total);
-    tg::k_bin_scatter<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist, d_start, d_wbase, d_queue, d_out, ld, d_keep, d_nlong);
+    tg::k_window_scan<<<1, 1024, 0, st>>>(d_wbase, n_windows, d_total, d_long_grouped);
+    tg::k_bin_scatter<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist, d_start, d_wbase, d_queue, d_out, ld, d_keep, d_nlong, d_long_grouped);
     const int64_t groups = (S + 31) / 32;
     const int64_t ctas = (groups + tg::kWarpsPerCta - 1) / tg::kWarpsPerCta;
     const unsigned grid = (unsigned)(ctas < c->sm_count ? ctas : c->sm_count);

@@ -38,6 +38,11 @@ def lengths_heavy_tail(rng, S, nmin=10, nmax=5000):
     return np.minimum(nmax, np.floor(nmin / u)).astype(np.int64)
 
 
+def lengths_log_uniform(rng, S, nmin=10, nmax=5000):
+    """n = floor(nmin (nmax/nmin)^U), U ~ Uniform[0,1): log-uniform on [nmin, nmax], mean ~ 803 (config 4 variant)."""
+    return np.minimum(nmax, np.floor(nmin * (nmax / nmin) ** rng.random(S))).astype(np.int64)
+
+
 def offsets_from_lengths(n):
     off = np.zeros(len(n) + 1, dtype=np.int64)
     np.cumsum(n, out=off[1:])
@@ -163,6 +168,9 @@ def torch_lengths(kind, S, seed, device):
     if kind == "heavy":
         u = 1.0 - torch.rand(S, generator=g, device=device, dtype=torch.float64)
         return torch.clamp(torch.floor(10.0 / u), max=5000.0).to(torch.int64)
+    if kind == "loguniform":
+        u = torch.rand(S, generator=g, device=device, dtype=torch.float64)
+        return torch.clamp(torch.floor(10.0 * torch.pow(torch.tensor(500.0, dtype=torch.float64, device=device), u)), max=5000.0).to(torch.int64)
     if kind == "uniform":
         return torch.randint(20, 120, (S,), generator=g, device=device, dtype=torch.int64)
     if kind == "fixed96":                      # every polyline 96 points = 36 whole 64-byte atoms (traffic probe)

@@ -262,6 +262,44 @@ def test_heavy_tail_at_scale_subsample(gpu_ctx):
     assert_table_close(out[:, torch.as_tensor(idx, device=dev)].T.cpu().numpy(), np.asarray(rows), "heavy subsample")
 
 
+def test_heavy_tail_long_row_of_the_queue(gpu_ctx):
+    """Same law at 800k polylines: more than 6144 polylines exceed 1024 points, so they take row 0 of the
+    queue (groups of nearly equal length, longest first) instead of the long-polyline kernel; two
+    polylines beyond the queue's 9216-point limit still go to that kernel.  Counts exact, the longest
+    polylines and a random subsample match the oracle, and the rows agree bit for bit with the SAME
+    polylines computed in a small table (where they take the long-polyline kernel or other groups)."""
+    import torch
+    dev = torch.device("cuda:0")
+    S = 800_000
+    n = synth.torch_lengths("heavy", S, 7, dev)
+    n[12345] = 9216; n[23456] = 9217; n[34567] = 12000; n[45678] = 1025; n[56789] = 1024
+    assert int((n > 1024).sum()) >= 6144
+    pts, off = synth.torch_random_walk_csr(n, 7, dev)
+    P = pts.shape[0]
+    out = torch.empty((17, S), dtype=torch.float64, device=dev)
+    keep = torch.empty(S, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    gpu_ctx.metrics_dev(pts.data_ptr(), _lib.F64, off.data_ptr(), S, P, out.data_ptr(), keep.data_ptr())
+    gpu_ctx.synchronize()
+    assert int((keep == 3).sum()) == S
+    special = np.array([12345, 23456, 34567, 45678, 56789])
+    idx = np.unique(np.concatenate([torch.topk(n, 40).indices.cpu().numpy(), special,
+                                    torch.nonzero((n > 1024) & (n < 5000)).flatten()[:120].cpu().numpy(),
+                                    np.random.default_rng(2).integers(0, S, 300)]))
+    off_h = off.cpu().numpy()
+    lines = [pts[off_h[s]:off_h[s + 1]].cpu().numpy() for s in idx]
+    got = out[:, torch.as_tensor(idx, device=dev)].T.cpu().numpy()
+    assert_table_close(got, np.asarray([so.metrics_row(l) for l in lines]), "heavy long-row subsample")
+    sub_pts, sub_off = synth.lines_to_csr(lines)                 # few long polylines here: long-polyline kernel
+    table, sub_keep = gpu_ctx.metrics_host(sub_pts, sub_off)[:2]
+    assert np.all(sub_keep == 3)
+    mism = np.nonzero(~np.all((got == table.T) | (np.isnan(got) & np.isnan(table.T)), axis=1))[0]
+    # the long-polyline kernel splits a polyline over 32 lanes and merges: same values to rounding, not bit-identical
+    short = np.array([len(l) <= 1024 for l in lines])
+    assert not np.any(short[mism]), "queued polylines must not depend on the table they are in"
+    assert_table_close(got, table.T, "long row vs long-polyline kernel")
+
+
 def test_degenerate_grid_polylines(gpu_ctx):
     """Integer-grid polylines (duplicate points, collinear triples, right angles, reversals): almost every
     one leaves the speculative path and is recomputed by the exact pipeline; inf / NaN-to-number / zero
