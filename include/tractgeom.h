@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 1
+#define TG_ABI_VERSION 2   /* 2: + tg_bundle_spread_dev, tg_metrics_csr_host_ex (version-1 entry points unchanged) */
 
 #define TG_N_METRICS 17
 enum tg_metric {                 /* tract_geom_proc.py:164-187 */
@@ -104,6 +104,17 @@ int tg_bundle_reduce_dev(tg_context* ctx, const double* d_out, const uint8_t* d_
                          const uint8_t* d_select, int64_t S, const int64_t* h_bundle_offsets,
                          int64_t B, double* d_sums, int64_t* d_counts, void* stream);
 
+/* OPT-IN spread of the same 13 bundle columns (not part of the reference's df_bundle:
+ * tract_geom_proc.py:193 defines `_safe_std` = np.nanstd and never calls it).  Call after
+ * tg_bundle_reduce_dev with the same table, mask and bundle table, passing its d_sums / d_counts.
+ *     d_spread float64[B x 13 x 3]  {np.nanstd (ddof 0, two-pass about the bundle mean), np.nanmin, np.nanmax}
+ *                                   over the kept rows; NaN where the column has no non-NaN entry;
+ *                                   a column holding +-inf has std NaN (inf - inf), like numpy. */
+int tg_bundle_spread_dev(tg_context* ctx, const double* d_out, const uint8_t* d_keep,
+                         const uint8_t* d_select, int64_t S, const int64_t* h_bundle_offsets,
+                         int64_t B, const double* d_sums, const int64_t* d_counts,
+                         double* d_spread, void* stream);
+
 /* HOST-buffer convenience calls (the end-to-end path: H2D + kernels + D2H, synchronous).
  * h_xyz / h_offsets / h_out / h_keep are host pointers (pinned is faster, pageable works).
  * h_out may be NULL when only bundle statistics are wanted (what the reference driver consumes,
@@ -111,6 +122,12 @@ int tg_bundle_reduce_dev(tg_context* ctx, const double* d_out, const uint8_t* d_
 int tg_metrics_csr_host(tg_context* ctx, const void* h_xyz, int xyz_dtype, const int64_t* h_offsets,
                         int64_t S, int64_t P, const int64_t* h_bundle_offsets, int64_t B,
                         double* h_out, uint8_t* h_keep, double* h_sums, int64_t* h_counts);
+
+/* tg_metrics_csr_host plus the opt-in spread: h_spread float64[B x 13 x 3] as in tg_bundle_spread_dev, or NULL. */
+int tg_metrics_csr_host_ex(tg_context* ctx, const void* h_xyz, int xyz_dtype, const int64_t* h_offsets,
+                           int64_t S, int64_t P, const int64_t* h_bundle_offsets, int64_t B,
+                           double* h_out, uint8_t* h_keep, double* h_sums, int64_t* h_counts,
+                           double* h_spread);
 
 /* Introspection for bench.py / tests: kernels launched by this context since creation. */
 int tg_launch_count(tg_context* ctx, int64_t* launches);

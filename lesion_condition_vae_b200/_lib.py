@@ -18,7 +18,7 @@ F64, F32 = 0, 1
 EXPORTS = (
     "tg_abi_version", "tg_last_error", "tg_device_count", "tg_create", "tg_destroy", "tg_synchronize",
     "tg_stream", "tg_host_alloc", "tg_host_free", "tg_metrics_csr_dev", "tg_bundle_reduce_dev",
-    "tg_metrics_csr_host", "tg_launch_count",
+    "tg_metrics_csr_host", "tg_launch_count", "tg_bundle_spread_dev", "tg_metrics_csr_host_ex",
 )
 
 
@@ -55,6 +55,8 @@ def load():
     lib.tg_bundle_reduce_dev.argtypes = [vp, vp, vp, vp, i64, vp, i64, vp, vp, vp]
     lib.tg_metrics_csr_host.argtypes = [vp, vp, i32, vp, i64, i64, vp, i64, vp, vp, vp, vp]
     lib.tg_launch_count.argtypes = [vp, C.POINTER(i64)]
+    lib.tg_bundle_spread_dev.argtypes = [vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp]
+    lib.tg_metrics_csr_host_ex.argtypes = [vp, vp, i32, vp, i64, i64, vp, i64, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
         if name not in ("tg_abi_version", "tg_last_error"):
@@ -120,11 +122,18 @@ class Context:
         check(self._lib.tg_bundle_reduce_dev(self._h, d_out, d_keep, d_select or None, S, _ptr(bo), len(bo) - 1,
                                              d_sums, d_counts, stream or None))
 
+    def bundle_spread_dev(self, d_out, d_keep, d_select, S, bundle_offsets, d_sums, d_counts, d_spread, stream=0):
+        """Opt-in {std, min, max} of the 13 bundle columns; call after :meth:`bundle_reduce_dev` (same arguments)."""
+        bo = np.ascontiguousarray(bundle_offsets, dtype=np.int64)
+        check(self._lib.tg_bundle_spread_dev(self._h, d_out, d_keep, d_select or None, S, _ptr(bo), len(bo) - 1,
+                                             d_sums, d_counts, d_spread, stream or None))
+
     # ---- host-buffer call: H2D + kernels + D2H, synchronous ----
-    def metrics_host(self, points, offsets, bundle_offsets=None, want_rows=True, out=None, keep=None):
+    def metrics_host(self, points, offsets, bundle_offsets=None, want_rows=True, out=None, keep=None, spread=None):
         """points (P,3) float64|float32 C-contiguous, offsets int64[S+1].
 
         ``out`` / ``keep``: optional preallocated result arrays (e.g. pinned memory).
+        ``spread``: optional float64 (B,13,3) array that receives the opt-in {std, min, max} per bundle column.
         Returns (out (17,S) float64 or None, keep uint8[S], sums (B,13), counts (B,14))."""
         points = np.ascontiguousarray(points)
         if points.dtype == np.float64:
@@ -149,6 +158,11 @@ class Context:
         assert keep.shape == (S,) and keep.dtype == np.uint8
         sums = np.empty((B, N_BUNDLE_COLS), dtype=np.float64)
         counts = np.empty((B, N_BUNDLE_COLS + 1), dtype=np.int64)
+        if spread is not None:
+            assert spread.shape == (B, N_BUNDLE_COLS, 3) and spread.dtype == np.float64 and spread.flags.c_contiguous
+            check(self._lib.tg_metrics_csr_host_ex(self._h, _ptr(points), code, _ptr(offsets), S, P, _ptr(bo), B,
+                                                   _ptr(out), _ptr(keep), _ptr(sums), _ptr(counts), _ptr(spread)))
+            return out, keep, sums, counts
         check(self._lib.tg_metrics_csr_host(self._h, _ptr(points), code, _ptr(offsets), S, P, _ptr(bo), B,
                                             _ptr(out), _ptr(keep), _ptr(sums), _ptr(counts)))
         return out, keep, sums, counts

@@ -103,7 +103,7 @@ constexpr int kBundleThreads = 256;
 constexpr int kBundleTile = 4096;
 constexpr int kNB = TG_N_BUNDLE_COLS;
 
-struct TileDesc { int64_t begin, end; };
+struct TileDesc { int64_t begin, end, bundle; };
 
 __constant__ int c_bundle_src[kNB];
 
@@ -191,6 +191,101 @@ k_bundle_final(const int64_t* __restrict__ tile_first, const double* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Kernel 3 (opt-in): spread of the 13 bundle columns — population standard
+// deviation (np.nanstd, what ref:193 `_safe_std` defines and never calls), minimum, maximum.
+// Two-pass like numpy: deviations from the bundle mean that kernel 2 produced.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBundleThreads)
+k_spread_tiles(const double* __restrict__ out, const uint8_t* __restrict__ keep, const uint8_t* __restrict__ select,
+               const int64_t S, const TileDesc* __restrict__ tiles, const double* __restrict__ sums, const int64_t* __restrict__ counts,
+               double* __restrict__ tspread) {
+    const TileDesc t = tiles[blockIdx.x];
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    double mean[kNB], ssq[kNB], lo[kNB], hi[kNB];
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) {
+        const int64_t c = counts[t.bundle * (kNB + 1) + 1 + j];
+        mean[j] = c > 0 ? sums[t.bundle * kNB + j] / (double)c : 0.0;
+        ssq[j] = 0.0; lo[j] = inf; hi[j] = -inf;
+    }
+    for (int64_t s = t.begin + threadIdx.x; s < t.end; s += kBundleThreads) {
+        bool on = (keep[s] & TG_KEEP_BOTH) == TG_KEEP_BOTH;
+        if (select != nullptr) on = on && (select[s] != 0);
+        if (!on) continue;
+#pragma unroll
+        for (int j = 0; j < kNB; ++j) {
+            const double v = __ldg(out + (int64_t)c_bundle_src[j] * S + s);
+            if (v == v) {
+                const double d = v - mean[j];                  // inf - inf = NaN, as in numpy
+                ssq[j] += d * d;
+                lo[j] = fmin(lo[j], v); hi[j] = fmax(hi[j], v);
+            }
+        }
+    }
+    __shared__ double s_part[kBundleThreads / 32][kNB][3];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < kNB; ++j) {
+        double v = ssq[j], a = lo[j], b = hi[j];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            v += __shfl_down_sync(0xffffffffu, v, o);
+            a = fmin(a, __shfl_down_sync(0xffffffffu, a, o));
+            b = fmax(b, __shfl_down_sync(0xffffffffu, b, o));
+        }
+        if (lane == 0) { s_part[warp][j][0] = v; s_part[warp][j][1] = a; s_part[warp][j][2] = b; }
+    }
+    __syncthreads();
+    if (threadIdx.x < kNB) {
+        double v = 0.0, a = inf, b = -inf;
+        for (int w = 0; w < kBundleThreads / 32; ++w) {
+            v += s_part[w][threadIdx.x][0];
+            a = fmin(a, s_part[w][threadIdx.x][1]);
+            b = fmax(b, s_part[w][threadIdx.x][2]);
+        }
+        double* dst = tspread + ((int64_t)blockIdx.x * kNB + threadIdx.x) * 3;
+        dst[0] = v; dst[1] = a; dst[2] = b;
+    }
+}
+
+// one CTA per bundle, fixed-order tree like k_bundle_final; spread[b][j] = {std, min, max}, NaN when the column
+// has no non-NaN entry.  A NaN partial (inf - inf) must survive the tree: fmin/fmax would drop it, the sum keeps it.
+__global__ void __launch_bounds__(kFinalThreads)
+k_spread_final(const int64_t* __restrict__ tile_first, const double* __restrict__ tspread, const int64_t* __restrict__ counts,
+               double* __restrict__ spread) {
+    __shared__ double s_v[kFinalThreads], s_a[kFinalThreads], s_b[kFinalThreads];
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const int64_t b = blockIdx.x;
+    const int64_t t0 = tile_first[b], t1 = tile_first[b + 1];
+    for (int j = 0; j < kNB; ++j) {
+        double v = 0.0, lo = inf, hi = -inf;
+        for (int64_t t = t0 + threadIdx.x; t < t1; t += kFinalThreads) {
+            const double* src = tspread + (t * kNB + j) * 3;
+            v += src[0]; lo = fmin(lo, src[1]); hi = fmax(hi, src[2]);
+        }
+        s_v[threadIdx.x] = v; s_a[threadIdx.x] = lo; s_b[threadIdx.x] = hi;
+        __syncthreads();
+        for (int o = kFinalThreads / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) {
+                s_v[threadIdx.x] += s_v[threadIdx.x + o];
+                s_a[threadIdx.x] = fmin(s_a[threadIdx.x], s_a[threadIdx.x + o]);
+                s_b[threadIdx.x] = fmax(s_b[threadIdx.x], s_b[threadIdx.x + o]);
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            const int64_t c = counts[b * (kNB + 1) + 1 + j];
+            double* dst = spread + (b * kNB + j) * 3;
+            dst[0] = c > 0 ? sqrt(s_v[0] / (double)c) : nan;
+            dst[1] = c > 0 ? s_a[0] : nan;
+            dst[2] = c > 0 ? s_b[0] : nan;
+        }
+        __syncthreads();
+    }
+}
+
 }  // namespace tg
 
 // ==============================================================================================
@@ -257,9 +352,9 @@ struct tg_context {
     bool grouped_ready = false;
     // bundle-reduce scratch
     PinBuf h_tiles;                   // TileDesc[nt] followed by int64 tile_first[B+1]
-    DevBuf d_tiles, d_tsum, d_tcnt;
+    DevBuf d_tiles, d_tsum, d_tcnt, d_tspread;
     // host-path scratch
-    DevBuf d_xyz, d_off, d_out, d_keep, d_sums, d_counts;
+    DevBuf d_xyz, d_off, d_out, d_keep, d_sums, d_counts, d_spread;
 };
 
 namespace {
@@ -290,6 +385,41 @@ int upload_bundle_src() {
     if (done_for == dev) return TG_OK;
     TG_CUDA(cudaMemcpyToSymbol(tg::c_bundle_src, TG_BUNDLE_SOURCE, sizeof(int) * TG_N_BUNDLE_COLS));
     done_for = dev;
+    return TG_OK;
+}
+
+// Tile table of a bundle partition: TileDesc[nt] (tiles never straddle bundles) followed by tile_first[B+1],
+// built in pinned memory and copied to the device on `st`.
+int plan_bundle_tiles(tg_context* c, const int64_t* h_bo, int64_t B, cudaStream_t st, int64_t* n_tiles,
+                      const tg::TileDesc** d_tiles, const int64_t** d_first) {
+    int64_t nt = 0;
+    for (int64_t b = 0; b < B; ++b) nt += (h_bo[b + 1] - h_bo[b] + tg::kBundleTile - 1) / tg::kBundleTile;
+    if (nt > 0x7fffffffLL || B > 0x7fffffffLL) return set_err(TG_E_INVALID, "too many tiles/bundles for one launch");
+    const size_t tiles_bytes = sizeof(tg::TileDesc) * (size_t)nt;
+    const size_t first_bytes = sizeof(int64_t) * (size_t)(B + 1);
+    int rc;
+    if (c->staged_pending) { TG_CUDA(cudaEventSynchronize(c->staged)); c->staged_pending = false; }
+    if ((rc = c->h_tiles.reserve(tiles_bytes + first_bytes))) return rc;
+    if ((rc = c->d_tiles.reserve(tiles_bytes + first_bytes))) return rc;
+    tg::TileDesc* ht = (tg::TileDesc*)c->h_tiles.p;
+    int64_t* hf = (int64_t*)((char*)c->h_tiles.p + tiles_bytes);
+    int64_t t = 0;
+    for (int64_t b = 0; b < B; ++b) {
+        hf[b] = t;
+        for (int64_t s = h_bo[b]; s < h_bo[b + 1]; s += tg::kBundleTile) {
+            ht[t].begin = s;
+            ht[t].end = (s + tg::kBundleTile < h_bo[b + 1]) ? s + tg::kBundleTile : h_bo[b + 1];
+            ht[t].bundle = b;
+            ++t;
+        }
+    }
+    hf[B] = t;
+    TG_CUDA(cudaMemcpyAsync(c->d_tiles.p, c->h_tiles.p, tiles_bytes + first_bytes, cudaMemcpyHostToDevice, st));
+    TG_CUDA(cudaEventRecord(c->staged, st));
+    c->staged_pending = true;
+    *n_tiles = nt;
+    *d_tiles = (const tg::TileDesc*)c->d_tiles.p;
+    *d_first = (const int64_t*)((const char*)c->d_tiles.p + tiles_bytes);
     return TG_OK;
 }
 
@@ -347,7 +477,7 @@ int tg_destroy(tg_context* c) {
     c->h_tiles.release();
     c->d_tiles.release(); c->d_tsum.release(); c->d_tcnt.release();
     c->d_xyz.release(); c->d_off.release(); c->d_out.release(); c->d_keep.release();
-    c->d_sums.release(); c->d_counts.release();
+    c->d_sums.release(); c->d_counts.release(); c->d_spread.release(); c->d_tspread.release();
     c->d_xyz64.release(); c->d_qhead.release(); c->d_hist.release(); c->d_start.release(); c->d_perm.release();
     if (c->s_copy) { cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_back); for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_h2d[i]); cudaEventDestroy(c->ev_comp[i]); } }
     cudaEventDestroy(c->staged);
@@ -483,32 +613,11 @@ int tg_bundle_reduce_dev(tg_context* c, const double* d_out, const uint8_t* d_ke
     if (rc) return rc;
 
     int64_t nt = 0;
-    for (int64_t b = 0; b < B; ++b) nt += (h_bo[b + 1] - h_bo[b] + tg::kBundleTile - 1) / tg::kBundleTile;
-    const size_t tiles_bytes = sizeof(tg::TileDesc) * (size_t)nt;
-    const size_t first_bytes = sizeof(int64_t) * (size_t)(B + 1);
-    if (c->staged_pending) { TG_CUDA(cudaEventSynchronize(c->staged)); c->staged_pending = false; }
-    if ((rc = c->h_tiles.reserve(tiles_bytes + first_bytes))) return rc;
-    if ((rc = c->d_tiles.reserve(tiles_bytes + first_bytes))) return rc;
+    const tg::TileDesc* dt = nullptr;
+    const int64_t* df = nullptr;
+    if ((rc = plan_bundle_tiles(c, h_bo, B, st, &nt, &dt, &df))) return rc;
     if ((rc = c->d_tsum.reserve(sizeof(double) * tg::kNB * (size_t)(nt + 1)))) return rc;
     if ((rc = c->d_tcnt.reserve(sizeof(int64_t) * (tg::kNB + 1) * (size_t)(nt + 1)))) return rc;
-    tg::TileDesc* ht = (tg::TileDesc*)c->h_tiles.p;
-    int64_t* hf = (int64_t*)((char*)c->h_tiles.p + tiles_bytes);
-    int64_t t = 0;
-    for (int64_t b = 0; b < B; ++b) {
-        hf[b] = t;
-        for (int64_t s = h_bo[b]; s < h_bo[b + 1]; s += tg::kBundleTile) {
-            ht[t].begin = s;
-            ht[t].end = (s + tg::kBundleTile < h_bo[b + 1]) ? s + tg::kBundleTile : h_bo[b + 1];
-            ++t;
-        }
-    }
-    hf[B] = t;
-    TG_CUDA(cudaMemcpyAsync(c->d_tiles.p, c->h_tiles.p, tiles_bytes + first_bytes, cudaMemcpyHostToDevice, st));
-    TG_CUDA(cudaEventRecord(c->staged, st));
-    c->staged_pending = true;
-    const tg::TileDesc* dt = (const tg::TileDesc*)c->d_tiles.p;
-    const int64_t* df = (const int64_t*)((const char*)c->d_tiles.p + tiles_bytes);
-    if (nt > 0x7fffffffLL || B > 0x7fffffffLL) return set_err(TG_E_INVALID, "too many tiles/bundles for one launch");
     if (nt > 0) {
         tg::k_bundle_tiles<<<(unsigned)nt, tg::kBundleThreads, 0, st>>>(d_out, d_keep, d_select, S, dt, (double*)c->d_tsum.p, (int64_t*)c->d_tcnt.p);
         c->launches += 1;
@@ -519,8 +628,42 @@ int tg_bundle_reduce_dev(tg_context* c, const double* d_out, const uint8_t* d_ke
     return TG_OK;
 }
 
+int tg_bundle_spread_dev(tg_context* c, const double* d_out, const uint8_t* d_keep, const uint8_t* d_select, int64_t S,
+                         const int64_t* h_bo, int64_t B, const double* d_sums, const int64_t* d_counts, double* d_spread, void* stream) {
+    if (!c) return set_err(TG_E_INVALID, "null context");
+    if (S < 0 || B < 0) return set_err(TG_E_INVALID, "negative size");
+    if (B == 0) return TG_OK;
+    if (!h_bo || !d_sums || !d_counts || !d_spread || (S > 0 && (!d_out || !d_keep))) return set_err(TG_E_INVALID, "null pointer");
+    if (h_bo[0] < 0 || h_bo[B] > S) return set_err(TG_E_INVALID, "bundle_offsets out of range");
+    for (int64_t b = 0; b < B; ++b)
+        if (h_bo[b + 1] < h_bo[b]) return set_err(TG_E_INVALID, "bundle_offsets must be non-decreasing");
+    DeviceGuard g(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    int rc = upload_bundle_src();
+    if (rc) return rc;
+    int64_t nt = 0;
+    const tg::TileDesc* dt = nullptr;
+    const int64_t* df = nullptr;
+    if ((rc = plan_bundle_tiles(c, h_bo, B, st, &nt, &dt, &df))) return rc;
+    if ((rc = c->d_tspread.reserve(sizeof(double) * 3 * tg::kNB * (size_t)(nt + 1)))) return rc;
+    if (nt > 0) {
+        tg::k_spread_tiles<<<(unsigned)nt, tg::kBundleThreads, 0, st>>>(d_out, d_keep, d_select, S, dt, d_sums, d_counts, (double*)c->d_tspread.p);
+        c->launches += 1;
+    }
+    tg::k_spread_final<<<(unsigned)B, tg::kFinalThreads, 0, st>>>(df, (const double*)c->d_tspread.p, d_counts, d_spread);
+    c->launches += 1;
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
 int tg_metrics_csr_host(tg_context* c, const void* h_xyz, int xyz_dtype, const int64_t* h_off, int64_t S, int64_t P,
                         const int64_t* h_bo, int64_t B, double* h_out, uint8_t* h_keep, double* h_sums, int64_t* h_counts) {
+    return tg_metrics_csr_host_ex(c, h_xyz, xyz_dtype, h_off, S, P, h_bo, B, h_out, h_keep, h_sums, h_counts, nullptr);
+}
+
+int tg_metrics_csr_host_ex(tg_context* c, const void* h_xyz, int xyz_dtype, const int64_t* h_off, int64_t S, int64_t P,
+                           const int64_t* h_bo, int64_t B, double* h_out, uint8_t* h_keep, double* h_sums, int64_t* h_counts,
+                           double* h_spread) {
     if (!c) return set_err(TG_E_INVALID, "null context");
     if (S < 0 || P < 0 || B < 0) return set_err(TG_E_INVALID, "negative size");
     if (xyz_dtype != TG_F64 && xyz_dtype != TG_F32) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64 or TG_F32");
@@ -563,6 +706,7 @@ int tg_metrics_csr_host(tg_context* c, const void* h_xyz, int xyz_dtype, const i
     if ((rc = c->d_keep.reserve((size_t)S))) return rc;
     if ((rc = c->d_sums.reserve(sizeof(double) * tg::kNB * (size_t)B))) return rc;
     if ((rc = c->d_counts.reserve(sizeof(int64_t) * (tg::kNB + 1) * (size_t)B))) return rc;
+    if (h_spread && (rc = c->d_spread.reserve(sizeof(double) * 3 * tg::kNB * (size_t)B))) return rc;
     if (!c->s_copy) {
         TG_CUDA(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
         TG_CUDA(cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking));
@@ -605,6 +749,11 @@ int tg_metrics_csr_host(tg_context* c, const void* h_xyz, int xyz_dtype, const i
         if ((rc = tg_bundle_reduce_dev(c, d_out, d_keep, nullptr, S, h_bo, B, (double*)c->d_sums.p, (int64_t*)c->d_counts.p, st))) return rc;
         TG_CUDA(cudaMemcpyAsync(h_sums, c->d_sums.p, sizeof(double) * tg::kNB * (size_t)B, cudaMemcpyDeviceToHost, st));
         TG_CUDA(cudaMemcpyAsync(h_counts, c->d_counts.p, sizeof(int64_t) * (tg::kNB + 1) * (size_t)B, cudaMemcpyDeviceToHost, st));
+        if (h_spread) {
+            if ((rc = tg_bundle_spread_dev(c, d_out, d_keep, nullptr, S, h_bo, B, (const double*)c->d_sums.p, (const int64_t*)c->d_counts.p,
+                                           (double*)c->d_spread.p, st))) return rc;
+            TG_CUDA(cudaMemcpyAsync(h_spread, c->d_spread.p, sizeof(double) * 3 * tg::kNB * (size_t)B, cudaMemcpyDeviceToHost, st));
+        }
     }
     TG_CUDA(cudaStreamSynchronize(c->s_copy));
     TG_CUDA(cudaStreamSynchronize(st));

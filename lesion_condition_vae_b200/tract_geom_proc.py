@@ -51,6 +51,15 @@ def read_streamlines_from_vtk(vtk_path: str, max_streamlines: Optional[int] = No
     return out
 
 
+BUNDLE_SOURCE = (  # df_sl column behind each of the 13 means
+    "length", "tortuosity", "curv_mean", "curv_energy", "torsion_mean", "bend_angle_mean", "elongation_ratio",
+    "planarity_ratio", "anisotropy_ratio", "ang_dispersion", "centroid_x", "centroid_y", "centroid_z",
+)
+# opt-in extra df_bundle columns, appended AFTER the reference's 14 so the default schema
+# read by classification.py:64-75 / correlation.py:70-75 never changes
+SPREAD_COLUMNS = tuple(f"{src}_{stat}" for src in BUNDLE_SOURCE for stat in ("std", "min", "max"))
+
+
 def _prefix_for(n_per_line, want, start=0):
     """Smallest end index e > start such that lines[start:e] holds `want` lines with n > 2."""
     cand = np.flatnonzero(n_per_line[start:] > 2)
@@ -59,7 +68,7 @@ def _prefix_for(n_per_line, want, start=0):
     return start + int(cand[want - 1]) + 1
 
 
-def streamline_table_csr(points, offsets, max_streamlines=None, ctx=None):
+def streamline_table_csr(points, offsets, max_streamlines=None, ctx=None, spread=None):
     """-> (out (17,S') float64, row_mask bool[S'], sums (13,), counts (14,)) for the processed prefix.
 
     ``row_mask`` marks the polylines that become df_sl rows.  With ``max_streamlines`` the
@@ -72,7 +81,7 @@ def streamline_table_csr(points, offsets, max_streamlines=None, ctx=None):
     points = np.asarray(points)
     S = len(offsets) - 1
     if max_streamlines is None:
-        out, keep, sums, counts = ctx.metrics_host(points, offsets)
+        out, keep, sums, counts = ctx.metrics_host(points, offsets, spread=spread)
         return out, keep == _lib.KEEP_BOTH, sums[0], counts[0]
     want = int(max_streamlines)
     # ref:22-24: the cap is tested after an append, so a cap <= 0 still admits one polyline
@@ -81,7 +90,7 @@ def streamline_table_csr(points, offsets, max_streamlines=None, ctx=None):
     end = _prefix_for(n_per_line, want)
     while True:
         # one bundle = the whole prefix, so the device reduction already covers exactly the rows
-        out, keep, sums, counts = ctx.metrics_host(points[:int(offsets[end])], offsets[:end + 1])
+        out, keep, sums, counts = ctx.metrics_host(points[:int(offsets[end])], offsets[:end + 1], spread=spread)
         have = int(((keep & _lib.KEEP_LOADER) != 0).sum())
         if have >= want or end >= S:
             break
@@ -91,8 +100,9 @@ def streamline_table_csr(points, offsets, max_streamlines=None, ctx=None):
     return out, keep == _lib.KEEP_BOTH, sums[0], counts[0]
 
 
-def frames_from_table(out, rows, sums, counts):
-    """Build (df_sl, df_bundle) exactly as ref:189-211 shapes them."""
+def frames_from_table(out, rows, sums, counts, spread=None):
+    """Build (df_sl, df_bundle) exactly as ref:189-211 shapes them (+ the opt-in spread columns when
+    ``spread`` (13,3) is given)."""
     n_rows = int(counts[0])
     if n_rows == 0:
         # ref:189,197: pd.DataFrame([]) has no columns, df_sl["length"] raises KeyError('length')
@@ -104,13 +114,20 @@ def frames_from_table(out, rows, sums, counts):
     bundle = {"n_streamlines": n_rows}
     for name, v in zip(BUNDLE_COLUMNS[1:], means):
         bundle[name] = float(v)
+    if spread is not None:
+        for name, v in zip(SPREAD_COLUMNS, np.asarray(spread, dtype=np.float64).reshape(-1)):
+            bundle[name] = float(v)
     return df_sl, pd.DataFrame([bundle])
 
 
-def compute_streamline_metrics_csr(points, offsets, max_streamlines: Optional[int] = None, ctx=None):
-    """Same contract as :func:`compute_streamline_metrics`, on an in-memory CSR tractogram."""
-    out, rows, sums, counts = streamline_table_csr(points, offsets, max_streamlines, ctx)
-    return frames_from_table(out, rows, sums, counts)
+def compute_streamline_metrics_csr(points, offsets, max_streamlines: Optional[int] = None, ctx=None, extra_stats=False):
+    """Same contract as :func:`compute_streamline_metrics`, on an in-memory CSR tractogram.
+
+    ``extra_stats=True`` appends 39 opt-in columns to df_bundle: np.nanstd / np.nanmin / np.nanmax of the 13
+    aggregated df_sl columns (``SPREAD_COLUMNS``), reduced on the device in the same call."""
+    spread = np.empty((1, _lib.N_BUNDLE_COLS, 3), dtype=np.float64) if extra_stats else None
+    out, rows, sums, counts = streamline_table_csr(points, offsets, max_streamlines, ctx, spread=spread)
+    return frames_from_table(out, rows, sums, counts, None if spread is None else spread[0])
 
 
 def compute_streamline_metrics(vtk_path: str, max_streamlines: Optional[int] = None) -> Tuple[pd.DataFrame, pd.DataFrame]:
@@ -119,7 +136,14 @@ def compute_streamline_metrics(vtk_path: str, max_streamlines: Optional[int] = N
     return compute_streamline_metrics_csr(points, offsets, max_streamlines)
 
 
-def compute_bundles_csr(points, offsets, bundle_offsets, ctx=None, want_rows=True):
+def compute_streamline_metrics_extended(vtk_path: str, max_streamlines: Optional[int] = None) -> Tuple[pd.DataFrame, pd.DataFrame]:
+    """:func:`compute_streamline_metrics` with the opt-in spread columns (``SPREAD_COLUMNS``) appended to
+    df_bundle.  A separate name, so the drop-in keeps the reference's exact signature and schema."""
+    points, offsets = vtk_io.read_polylines_csr(vtk_path)
+    return compute_streamline_metrics_csr(points, offsets, max_streamlines, extra_stats=True)
+
+
+def compute_bundles_csr(points, offsets, bundle_offsets, ctx=None, want_rows=True, extra_stats=False):
     """Many bundles in ONE launch (BASELINE config 2: 16 tracts x 4 timepoints).
 
     Returns a list of (df_sl | None, df_bundle | None) per bundle; a bundle with no surviving
@@ -127,7 +151,8 @@ def compute_bundles_csr(points, offsets, bundle_offsets, ctx=None, want_rows=Tru
     reference driver would have skipped it (comprehensive_tract_geometry_analysis.py:129-131)."""
     ctx = ctx or _lib.default_context()
     bo = np.asarray(bundle_offsets, dtype=np.int64)
-    out, keep, sums, counts = ctx.metrics_host(points, offsets, bo, want_rows=want_rows)
+    spread = np.empty((len(bo) - 1, _lib.N_BUNDLE_COLS, 3), dtype=np.float64) if extra_stats else None
+    out, keep, sums, counts = ctx.metrics_host(points, offsets, bo, want_rows=want_rows, spread=spread)
     res = []
     for b in range(len(bo) - 1):
         if counts[b, 0] == 0:
@@ -135,9 +160,11 @@ def compute_bundles_csr(points, offsets, bundle_offsets, ctx=None, want_rows=Tru
             continue
         lo, hi = int(bo[b]), int(bo[b + 1])
         if want_rows:
-            df_sl, df_b = frames_from_table(out[:, lo:hi], keep[lo:hi] == _lib.KEEP_BOTH, sums[b], counts[b])
+            df_sl, df_b = frames_from_table(out[:, lo:hi], keep[lo:hi] == _lib.KEEP_BOTH, sums[b], counts[b],
+                                            None if spread is None else spread[b])
         else:
-            _, df_b = frames_from_table(np.empty((17, 0)), np.zeros(0, bool), sums[b], counts[b])
+            _, df_b = frames_from_table(np.empty((17, 0)), np.zeros(0, bool), sums[b], counts[b],
+                                        None if spread is None else spread[b])
             df_sl = None
         res.append((df_sl, df_b))
     return res

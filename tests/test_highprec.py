@@ -1,0 +1,91 @@
+"""High-precision referee for the three eigenvalue ratios (SURVEY.md §8c "what the build must add", N7).
+
+elongation = l1/l2, planarity = l2/l3 and anisotropy = l1/(l1+l2+l3+1e-12) come from the eigenvalues
+of a 3x3 covariance (/root/reference/src/geometry/tract_geom_proc.py:119-141).  On nearly straight
+polylines l1/l3 reaches 1e10 and LAPACK's own error in l3 is ~1e-16 l1, i.e. a RELATIVE error of
+~1e-16 l1/l3 in the ratios — the reason tests/parity_rules.py widens their tolerance to
+2e-14 l1/l3 beyond 1e-9.  Here the same ratios are recomputed from the float64 points in 60-digit
+arithmetic (mpmath), so that the oracle and the CUDA path are each judged against the true value
+instead of against each other:
+  * CPU: the oracle stays inside that envelope (the widening is justified, and not loose by orders
+    of magnitude on well-conditioned polylines);
+  * GPU: the CUDA path stays inside it too, and inside the strict 1e-9 rule wherever l1/l3 <= 1e5.
+"""
+import numpy as np
+import pytest
+
+mp = pytest.importorskip("mpmath")
+
+from lesion_condition_vae_b200 import synth
+from oracle import streamline_oracle as so
+
+SIGMAS = (0.2, 0.05, 5e-3, 5e-4, 5e-5, 5e-6)          # l1/l3 from ~1e2 to ~1e10
+
+
+def true_ratios(line):
+    """(elongation, planarity, anisotropy, l1/l3) of one polyline in 60-digit arithmetic."""
+    mp.mp.dps = 60
+    n = len(line)
+    cols = [[mp.mpf(float(v)) for v in line[:, j]] for j in range(3)]
+    mean = [mp.fsum(c) / n for c in cols]
+    C = mp.matrix(3, 3)
+    for a in range(3):
+        for b in range(a, 3):
+            v = mp.fsum((cols[a][i] - mean[a]) * (cols[b][i] - mean[b]) for i in range(n)) / (n - 1)
+            C[a, b] = v
+            C[b, a] = v
+    lam = sorted((mp.eigsy(C, eigvals_only=True)[i] for i in range(3)), reverse=True)
+    l1, l2, l3 = lam
+    eps = mp.mpf("1e-12")
+    elong = mp.inf if l2 <= eps else l1 / l2
+    plan = mp.inf if l3 <= eps else l2 / l3
+    return float(elong), float(plan), float(l1 / (l1 + l2 + l3 + eps)), float(l1 / l3)
+
+
+def cases():
+    lines = []
+    for j, sigma in enumerate(SIGMAS):
+        n = np.array([24, 60, 100, 100, 180, 400])
+        pts, off = synth.random_walk_csr(n, seed=900 + j, sigma=sigma)
+        lines += [pts[off[i]:off[i + 1]] for i in range(len(n))]
+    return lines
+
+
+def judge(got, lines, strict_only=False):
+    """Max over polylines of |got - true| / tolerance for the 3 ratios; tolerance = max(1e-9, 2e-14 l1/l3) relative
+    (anisotropy: 1e-9 always: it does not involve the small eigenvalues)."""
+    worst = np.zeros(3)
+    conds = []
+    for row, line in zip(got, lines):
+        e, p, a, cond = true_ratios(line)
+        conds.append(cond)
+        if strict_only and cond > 1e5:
+            continue
+        wide = max(1e-9, 2e-14 * cond)
+        for k, (g, t, tol) in enumerate(((row[10], e, wide), (row[11], p, wide), (row[12], a, 1e-9))):
+            assert np.isfinite(t) and np.isfinite(g)
+            worst[k] = max(worst[k], abs(g - t) / (tol * abs(t)))
+    return worst, np.asarray(conds)
+
+
+def test_oracle_eigen_ratios_against_60_digit_arithmetic():
+    lines = cases()
+    got = np.asarray([so.metrics_row(l) for l in lines])
+    worst, conds = judge(got, lines)
+    assert conds.min() < 1e4 and conds.max() > 1e8            # the cases span both regimes of the rule
+    assert np.all(worst <= 1.0), f"oracle outside max(1e-9, 2e-14 l1/l3): error/tolerance = {worst}"
+    strict, _ = judge(got, lines, strict_only=True)
+    assert np.all(strict <= 0.05), f"oracle is >= 20x inside 1e-9 where l1/l3 <= 1e5 (error ~1e-16 l1/l3): {strict}"
+
+
+@pytest.mark.gpu
+def test_gpu_eigen_ratios_against_60_digit_arithmetic(gpu_ctx):
+    lines = cases()
+    pts, off = synth.lines_to_csr(lines)
+    table, keep = gpu_ctx.metrics_host(pts, off)[:2]
+    assert np.all(keep == 3)
+    got = table.T
+    worst, _ = judge(got, lines)
+    assert np.all(worst <= 1.0), f"CUDA path outside max(1e-9, 2e-14 l1/l3): error/tolerance = {worst}"
+    strict, _ = judge(got, lines, strict_only=True)
+    assert np.all(strict <= 1.0), f"CUDA path outside 1e-9 where l1/l3 <= 1e5: {strict}"

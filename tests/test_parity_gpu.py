@@ -150,6 +150,91 @@ def test_batched_bundles_match_per_bundle_calls(gpu_ctx, golden):
         assert_bundle_close(df_b.iloc[0].to_numpy(float), c["bundle"], c["sl"], nm)
 
 
+def test_opt_in_bundle_spread_columns(gpu_ctx, golden):
+    """std / min / max of the 13 bundle columns as OPT-IN extra columns.  The default
+    df_bundle keeps the reference's 14 columns; the 39 extras equal np.nanstd / np.nanmin / np.nanmax
+    (what ref:193 `_safe_std` defines) over the oracle's df_sl, NaN skipped, inf kept (std NaN then)."""
+    import warnings
+    from parity_rules import ATOL, BUNDLE_SOURCE, RTOL
+    names = ["config2_t0_tp0", "config2_t3_tp1", "config2_t7_tp2"]
+    lines = []
+    bo = [0]
+    for nm in names:
+        c = golden[nm]
+        lines += [c["points"][c["offsets"][i]:c["offsets"][i + 1]] for i in range(len(c["offsets"]) - 1)]
+        bo.append(len(lines))
+    # bundle 3: a straight line (elongation / planarity = inf), a planar arc, short and dropped polylines
+    t = np.linspace(0.0, 1.0, 30)
+    extra = [np.outer(t, [3.0, 4.0, 12.0]), np.stack([np.cos(t), np.sin(t), 0 * t], axis=1) * 20.0,
+             np.zeros((2, 3)), synth.random_walk_csr(np.array([40]), seed=77)[0], np.ones((5, 3))]
+    lines += extra
+    bo += [len(lines), len(lines)]                                   # + an empty bundle
+    pts, off = synth.lines_to_csr(lines)
+    bo = np.asarray(bo, dtype=np.int64)
+    plain = tgp.compute_bundles_csr(pts, off, bo, ctx=gpu_ctx)
+    full = tgp.compute_bundles_csr(pts, off, bo, ctx=gpu_ctx, extra_stats=True)
+    assert full[4] == (None, None)
+    for b in range(4):
+        df_sl, df_b = full[b]
+        assert list(plain[b][1].columns) == list(tgp.BUNDLE_COLUMNS)                       # default schema untouched
+        assert list(df_b.columns) == list(tgp.BUNDLE_COLUMNS) + list(tgp.SPREAD_COLUMNS)
+        assert df_b.iloc[0, :14].equals(plain[b][1].iloc[0])
+        p, o = synth.lines_to_csr(lines[bo[b]:bo[b + 1]])
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ref_sl, _ = so.compute_streamline_metrics_csr(p, o)
+            for j, src in enumerate(BUNDLE_SOURCE):
+                col = ref_sl[src].to_numpy()
+                exp = (np.nanstd(col), np.nanmin(col), np.nanmax(col))
+                for stat, e in zip(("std", "min", "max"), exp):
+                    g = float(df_b[f"{src}_{stat}"].iloc[0])
+                    if not np.isfinite(e):
+                        assert (np.isnan(e) and np.isnan(g)) or g == e, (b, src, stat, g, e)
+                        continue
+                    rtol = RTOL
+                    if src in ("elongation_ratio", "planarity_ratio"):
+                        cond = (ref_sl["elongation_ratio"] * ref_sl["planarity_ratio"]).to_numpy()
+                        cond = cond[np.isfinite(cond)]
+                        rtol = max(RTOL, 2e-14 * float(cond.max())) if len(cond) else RTOL
+                    assert abs(g - e) <= rtol * max(abs(e), float(np.nanmax(np.abs(col)))) + ATOL[src], (b, src, stat, g, e)
+    # bundle 3 really exercised the special values
+    assert np.isinf(full[3][1]["elongation_ratio_max"].iloc[0]) and np.isnan(full[3][1]["elongation_ratio_std"].iloc[0])
+    # single-file entry points: reference signature unchanged, extended variant separate
+    df_sl, df_b = tgp.compute_streamline_metrics_csr(pts[:off[bo[1]]], off[:bo[1] + 1], ctx=gpu_ctx, extra_stats=True)
+    assert df_b.shape == (1, 14 + 39) and df_b.iloc[0].equals(full[0][1].iloc[0])
+
+
+def test_bundle_spread_device_abi_with_mask(gpu_ctx):
+    """tg_bundle_spread_dev on a device-resident table with a selection mask: equals numpy on the selected rows."""
+    import torch
+    dev = torch.device("cuda:0")
+    S = 30_000
+    n = synth.torch_lengths("uniform", S, 11, dev)
+    pts, off = synth.torch_random_walk_csr(n, 11, dev)
+    out = torch.empty((17, S), dtype=torch.float64, device=dev)
+    keep = torch.empty(S, dtype=torch.uint8, device=dev)
+    gpu_ctx.metrics_dev(pts.data_ptr(), _lib.F64, off.data_ptr(), S, pts.shape[0], out.data_ptr(), keep.data_ptr())
+    sel = (torch.arange(S, device=dev) % 3 != 0).to(torch.uint8)
+    bo = np.array([0, 9_000, 9_000, 21_500, S], dtype=np.int64)
+    B = len(bo) - 1
+    sums = torch.empty((B, 13), dtype=torch.float64, device=dev)
+    counts = torch.empty((B, 14), dtype=torch.int64, device=dev)
+    spread = torch.empty((B, 13, 3), dtype=torch.float64, device=dev)
+    gpu_ctx.bundle_reduce_dev(out.data_ptr(), keep.data_ptr(), sel.data_ptr(), S, bo, sums.data_ptr(), counts.data_ptr())
+    gpu_ctx.bundle_spread_dev(out.data_ptr(), keep.data_ptr(), sel.data_ptr(), S, bo, sums.data_ptr(), counts.data_ptr(), spread.data_ptr())
+    gpu_ctx.synchronize()
+    table, mask, got = out.cpu().numpy(), sel.cpu().numpy().astype(bool), spread.cpu().numpy()
+    src = (0, 2, 4, 6, 7, 8, 10, 11, 12, 16, 13, 14, 15)
+    for b in range(B):
+        rows = table[:, bo[b]:bo[b + 1]][:, mask[bo[b]:bo[b + 1]]]
+        if rows.shape[1] == 0:
+            assert np.isnan(got[b]).all()
+            continue
+        for j, m in enumerate(src):
+            col = rows[m]
+            np.testing.assert_allclose(got[b, j], [np.std(col), col.min(), col.max()], rtol=1e-12, atol=1e-15)
+
+
 def test_device_pointer_abi_and_size_independent_properties(gpu_ctx):
     """Device-resident call at a size the oracle cannot cover, checked through invariances:
     rigid translation leaves every metric but the centroid unchanged (to rounding), reversing each
