@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 2   /* 2: + tg_bundle_spread_dev, tg_metrics_csr_host_ex (version-1 entry points unchanged) */
+#define TG_ABI_VERSION 2   /* 2: + tg_bundle_spread_dev, tg_metrics_csr_host_ex, tg_resample_csr_* (version-1 entry points unchanged) */
 
 #define TG_N_METRICS 17
 enum tg_metric {                 /* tract_geom_proc.py:164-187 */
@@ -128,6 +128,17 @@ int tg_metrics_csr_host_ex(tg_context* ctx, const void* h_xyz, int xyz_dtype, co
                            int64_t S, int64_t P, const int64_t* h_bundle_offsets, int64_t B,
                            double* h_out, uint8_t* h_keep, double* h_sums, int64_t* h_counts,
                            double* h_spread);
+
+/* Arc-length resampling of every polyline to n_nodes points: the ragged-to-fixed step in
+ * front of src/vae/data_loader.py:94-100, which expects exactly 100 `point_id`s per streamline and for which
+ * the reference ships no producer.  Node k lies at arc length k L/(n_nodes-1), linearly interpolated inside
+ * its segment; node 0 / node n_nodes-1 are the first / last point.  nodes: float64[S x n_nodes x 3].
+ * A polyline of zero length (or one point) repeats its first point; an empty polyline, or one holding a
+ * non-finite coordinate, gives NaN nodes.  n_nodes >= 2. */
+int tg_resample_csr_dev(tg_context* ctx, const void* d_xyz, int xyz_dtype, const int64_t* d_offsets,
+                        int64_t S, int64_t P, int n_nodes, double* d_nodes, void* stream);
+int tg_resample_csr_host(tg_context* ctx, const void* h_xyz, int xyz_dtype, const int64_t* h_offsets,
+                         int64_t S, int64_t P, int n_nodes, double* h_nodes);
 
 /* Introspection for bench.py / tests: kernels launched by this context since creation. */
 int tg_launch_count(tg_context* ctx, int64_t* launches);

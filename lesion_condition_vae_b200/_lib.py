@@ -19,6 +19,7 @@ EXPORTS = (
     "tg_abi_version", "tg_last_error", "tg_device_count", "tg_create", "tg_destroy", "tg_synchronize",
     "tg_stream", "tg_host_alloc", "tg_host_free", "tg_metrics_csr_dev", "tg_bundle_reduce_dev",
     "tg_metrics_csr_host", "tg_launch_count", "tg_bundle_spread_dev", "tg_metrics_csr_host_ex",
+    "tg_resample_csr_dev", "tg_resample_csr_host",
 )
 
 
@@ -56,6 +57,8 @@ def load():
     lib.tg_metrics_csr_host.argtypes = [vp, vp, i32, vp, i64, i64, vp, i64, vp, vp, vp, vp]
     lib.tg_launch_count.argtypes = [vp, C.POINTER(i64)]
     lib.tg_bundle_spread_dev.argtypes = [vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp]
+    lib.tg_resample_csr_dev.argtypes = [vp, vp, i32, vp, i64, i64, i32, vp, vp]
+    lib.tg_resample_csr_host.argtypes = [vp, vp, i32, vp, i64, i64, i32, vp]
     lib.tg_metrics_csr_host_ex.argtypes = [vp, vp, i32, vp, i64, i64, vp, i64, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
@@ -127,6 +130,26 @@ class Context:
         bo = np.ascontiguousarray(bundle_offsets, dtype=np.int64)
         check(self._lib.tg_bundle_spread_dev(self._h, d_out, d_keep, d_select or None, S, _ptr(bo), len(bo) - 1,
                                              d_sums, d_counts, d_spread, stream or None))
+
+    def resample_dev(self, d_xyz, dtype_code, d_offsets, S, P, n_nodes, d_nodes, stream=0):
+        check(self._lib.tg_resample_csr_dev(self._h, d_xyz, dtype_code, d_offsets, S, P, n_nodes, d_nodes, stream or None))
+
+    def resample_host(self, points, offsets, n_nodes=100, nodes=None):
+        """Arc-length resampling to ``n_nodes`` points per polyline -> float64 (S, n_nodes, 3)."""
+        points = np.ascontiguousarray(points)
+        if points.dtype == np.float32:
+            code = F32
+        else:
+            points = np.ascontiguousarray(points, dtype=np.float64)
+            code = F64
+        offsets = np.ascontiguousarray(offsets, dtype=np.int64)
+        S = len(offsets) - 1
+        P = points.shape[0] if points.ndim == 2 else points.size // 3
+        if nodes is None:
+            nodes = np.empty((S, n_nodes, 3), dtype=np.float64)
+        assert nodes.shape == (S, n_nodes, 3) and nodes.dtype == np.float64 and nodes.flags.c_contiguous
+        check(self._lib.tg_resample_csr_host(self._h, _ptr(points), code, _ptr(offsets), S, P, int(n_nodes), _ptr(nodes)))
+        return nodes
 
     # ---- host-buffer call: H2D + kernels + D2H, synchronous ----
     def metrics_host(self, points, offsets, bundle_offsets=None, want_rows=True, out=None, keep=None, spread=None):

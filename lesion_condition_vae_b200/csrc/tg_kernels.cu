@@ -286,6 +286,91 @@ k_spread_final(const int64_t* __restrict__ tile_first, const double* __restrict_
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Kernel 4: arc-length resampling of every polyline to K nodes — the ragged-to-fixed
+// step that would feed /root/reference/src/vae/data_loader.py:94-100 (exactly 100 `point_id`s per
+// streamline; the reference ships no producer).  Node k lies at arc length k L/(K-1) on the polyline,
+// linearly interpolated inside its segment; node K-1 is the last point itself.
+// One WARP per polyline, two passes over its points (the second one hits L1/L2): pass 1 = total length,
+// pass 2 = every lane owns one segment [c0, c1) of the cumulative length and emits the nodes inside it.
+// c1 of lane i and c0 of lane i+1 are the SAME double (shuffled, never recomputed), so every node is
+// emitted exactly once.  HBM-bound: 24 n bytes read, 24 K bytes written per polyline.
+// ------------------------------------------------------------------------------------------
+constexpr int kResampleThreads = 256;
+
+__device__ __forceinline__ double warp_scan_inclusive(double v, const int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(kResampleThreads)
+k_resample(const double* __restrict__ xyz, const int64_t* __restrict__ offsets, const int64_t S, const int K,
+           double* __restrict__ nodes) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * (kResampleThreads / 32);
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    for (int64_t s = (int64_t)blockIdx.x * (kResampleThreads / 32) + (threadIdx.x >> 5); s < S; s += warps_total) {
+        const int64_t o0 = __ldg(offsets + s);
+        const int64_t n = __ldg(offsets + s + 1) - o0;
+        const double* p = xyz + 3 * o0;
+        double* dst = nodes + (int64_t)s * K * 3;
+        // ---- pass 1: total length (lane partial sums, one tree at the end).  It only has to be CLOSE to the
+        //      last cumulative length of pass 2: the nodes 0..K-2 lie at k L/(K-1) <= L (1 - 1/(K-1)).
+        double part = 0.0;
+        for (int64_t i = lane; i < n - 1; i += 32) {
+            const double dx = p[3 * i + 3] - p[3 * i], dy = p[3 * i + 4] - p[3 * i + 1], dz = p[3 * i + 5] - p[3 * i + 2];
+            part += sqrt_fast((dx * dx + dy * dy) + dz * dz);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+        const double L = part;
+        if (!(L > 0.0) || !(L < __longlong_as_double(0x7ff0000000000000LL))) {
+            // no point: NaN; zero length (or a single point): every node is the first point; non-finite length: NaN
+            const bool first = n > 0 && L == 0.0;
+            const double x = first ? p[0] : nan, y = first ? p[1] : nan, z = first ? p[2] : nan;
+            for (int k = lane; k < K; k += 32) { dst[3 * k] = x; dst[3 * k + 1] = y; dst[3 * k + 2] = z; }
+            continue;
+        }
+        const double step = L / (double)(K - 1);
+        const double inv_step = (double)(K - 1) / L;
+        // ---- pass 2: emit
+        double carry = 0.0;
+        for (int64_t base = 0; base < n - 1; base += 32) {
+            const int64_t i = base + lane;
+            double seg = 0.0, ax = 0.0, ay = 0.0, az = 0.0, dx = 0.0, dy = 0.0, dz = 0.0;
+            if (i < n - 1) {
+                ax = p[3 * i]; ay = p[3 * i + 1]; az = p[3 * i + 2];
+                dx = p[3 * i + 3] - ax; dy = p[3 * i + 4] - ay; dz = p[3 * i + 5] - az;
+                seg = sqrt_fast((dx * dx + dy * dy) + dz * dz);
+            }
+            const double c1 = carry + warp_scan_inclusive(seg, lane);
+            double c0 = __shfl_up_sync(0xffffffffu, c1, 1);
+            if (lane == 0) c0 = carry;
+            carry = __shfl_sync(0xffffffffu, c1, 31);
+            if (i < n - 1 && c1 > c0) {
+                // first node index with k * step >= c0 (the product is only a guess: settle it with exact comparisons)
+                int k = min(max(__double2int_ru(c0 * inv_step), 0), K);
+                while (k > 0 && (double)(k - 1) * step >= c0) --k;
+                while (k < K - 1 && (double)k * step < c0) ++k;
+                const double inv = rcp_fast(c1 - c0);
+                for (; k < K - 1; ++k) {
+                    const double t = (double)k * step;
+                    if (!(t < c1)) break;
+                    const double r = fmin(fmax((t - c0) * inv, 0.0), 1.0);
+                    dst[3 * k] = ax + r * dx; dst[3 * k + 1] = ay + r * dy; dst[3 * k + 2] = az + r * dz;
+                }
+            }
+        }
+        if (lane == 0) {                                           // the last node is the last point itself
+            dst[3 * (K - 1)] = p[3 * (n - 1)]; dst[3 * (K - 1) + 1] = p[3 * (n - 1) + 1]; dst[3 * (K - 1) + 2] = p[3 * (n - 1) + 2];
+        }
+    }
+}
+
 }  // namespace tg
 
 // ==============================================================================================
@@ -354,7 +439,7 @@ struct tg_context {
     PinBuf h_tiles;                   // TileDesc[nt] followed by int64 tile_first[B+1]
     DevBuf d_tiles, d_tsum, d_tcnt, d_tspread;
     // host-path scratch
-    DevBuf d_xyz, d_off, d_out, d_keep, d_sums, d_counts, d_spread;
+    DevBuf d_xyz, d_off, d_out, d_keep, d_sums, d_counts, d_spread, d_nodes;
 };
 
 namespace {
@@ -477,7 +562,7 @@ int tg_destroy(tg_context* c) {
     c->h_tiles.release();
     c->d_tiles.release(); c->d_tsum.release(); c->d_tcnt.release();
     c->d_xyz.release(); c->d_off.release(); c->d_out.release(); c->d_keep.release();
-    c->d_sums.release(); c->d_counts.release(); c->d_spread.release(); c->d_tspread.release();
+    c->d_sums.release(); c->d_counts.release(); c->d_spread.release(); c->d_tspread.release(); c->d_nodes.release();
     c->d_xyz64.release(); c->d_qhead.release(); c->d_hist.release(); c->d_start.release(); c->d_perm.release();
     if (c->s_copy) { cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_back); for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_h2d[i]); cudaEventDestroy(c->ev_comp[i]); } }
     cudaEventDestroy(c->staged);
@@ -653,6 +738,59 @@ int tg_bundle_spread_dev(tg_context* c, const double* d_out, const uint8_t* d_ke
     tg::k_spread_final<<<(unsigned)B, tg::kFinalThreads, 0, st>>>(df, (const double*)c->d_tspread.p, d_counts, d_spread);
     c->launches += 1;
     TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_resample_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const int64_t* d_offsets, int64_t S, int64_t P,
+                        int n_nodes, double* d_nodes, void* stream) {
+    if (!c) return set_err(TG_E_INVALID, "null context");
+    if (S < 0 || P < 0) return set_err(TG_E_INVALID, "negative size");
+    if (n_nodes < 2) return set_err(TG_E_INVALID, "n_nodes must be at least 2");
+    if (xyz_dtype != TG_F64 && xyz_dtype != TG_F32) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64 or TG_F32");
+    if (S == 0) return TG_OK;
+    if (!d_offsets || !d_nodes || (P > 0 && !d_xyz)) return set_err(TG_E_INVALID, "null device pointer");
+    DeviceGuard g(c->device);
+    cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+    int rc;
+    if (xyz_dtype == TG_F32) {
+        if ((rc = c->d_xyz64.reserve(sizeof(double) * 3 * (size_t)P + 64))) return rc;
+        if ((rc = upcast_f32(c, d_xyz, 3 * P, (double*)c->d_xyz64.p, st))) return rc;
+        d_xyz = c->d_xyz64.p;
+    }
+    if (((uintptr_t)d_xyz & 7u) != 0) return set_err(TG_E_INVALID, "xyz must be 8-byte aligned");
+    const int64_t warps_per_cta = tg::kResampleThreads / 32;
+    const int64_t want = (S + warps_per_cta - 1) / warps_per_cta;
+    const int64_t cap = (int64_t)c->sm_count * (2048 / tg::kResampleThreads);
+    tg::k_resample<<<(unsigned)(want < cap ? want : cap), tg::kResampleThreads, 0, st>>>((const double*)d_xyz, d_offsets, S, n_nodes, d_nodes);
+    c->launches += 1;
+    TG_CUDA(cudaGetLastError());
+    return TG_OK;
+}
+
+int tg_resample_csr_host(tg_context* c, const void* h_xyz, int xyz_dtype, const int64_t* h_off, int64_t S, int64_t P,
+                         int n_nodes, double* h_nodes) {
+    if (!c) return set_err(TG_E_INVALID, "null context");
+    if (S < 0 || P < 0) return set_err(TG_E_INVALID, "negative size");
+    if (n_nodes < 2) return set_err(TG_E_INVALID, "n_nodes must be at least 2");
+    if (xyz_dtype != TG_F64 && xyz_dtype != TG_F32) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64 or TG_F32");
+    if (S == 0) return TG_OK;
+    if (!h_off || !h_nodes || (P > 0 && !h_xyz)) return set_err(TG_E_INVALID, "null pointer");
+    if (h_off[0] < 0 || h_off[S] > P) return set_err(TG_E_INVALID, "offsets out of range of the point array");
+    for (int64_t s = 0; s < S; ++s)
+        if (h_off[s + 1] < h_off[s]) return set_err(TG_E_INVALID, "offsets must be non-decreasing");
+    DeviceGuard g(c->device);
+    const size_t esz = xyz_dtype == TG_F64 ? 8 : 4;
+    const size_t node_bytes = sizeof(double) * 3 * (size_t)n_nodes * (size_t)S;
+    int rc;
+    if ((rc = c->d_xyz.reserve(esz * 3 * (size_t)P + 64))) return rc;
+    if ((rc = c->d_off.reserve(sizeof(int64_t) * (size_t)(S + 1)))) return rc;
+    if ((rc = c->d_nodes.reserve(node_bytes))) return rc;
+    cudaStream_t st = c->stream;
+    if (P > 0) TG_CUDA(cudaMemcpyAsync(c->d_xyz.p, h_xyz, esz * 3 * (size_t)P, cudaMemcpyHostToDevice, st));
+    TG_CUDA(cudaMemcpyAsync(c->d_off.p, h_off, sizeof(int64_t) * (size_t)(S + 1), cudaMemcpyHostToDevice, st));
+    if ((rc = tg_resample_csr_dev(c, c->d_xyz.p, xyz_dtype, (const int64_t*)c->d_off.p, S, P, n_nodes, (double*)c->d_nodes.p, st))) return rc;
+    TG_CUDA(cudaMemcpyAsync(h_nodes, c->d_nodes.p, node_bytes, cudaMemcpyDeviceToHost, st));
+    TG_CUDA(cudaStreamSynchronize(st));
     return TG_OK;
 }
 
