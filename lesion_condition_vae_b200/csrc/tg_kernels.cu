@@ -296,7 +296,17 @@ k_spread_final(const int64_t* __restrict__ tile_first, const double* __restrict_
 // c1 of lane i and c0 of lane i+1 are the SAME double (shuffled, never recomputed), so every node is
 // emitted exactly once.  HBM-bound: 24 n bytes read, 24 K bytes written per polyline.
 // ------------------------------------------------------------------------------------------
-constexpr int kResampleThreads = 256;
+constexpr int kRsWarps = 8;
+constexpr int kResampleThreads = kRsWarps * 32;
+constexpr int kRsBatch = 1;                               // polylines per warp iteration
+constexpr int kRsMaxN = 129;                              // staged path: polylines of up to 129 points (4 chunks of 32 segments)
+constexpr int kRsMaxK = 128;                              // ... resampled to at most 128 nodes
+constexpr int kRsInBytes = ((kRsMaxN * 24 + 8 + 15) / 16) * 16 + 16;   // 8 bytes of skew in front, whole 16-byte pieces
+constexpr int kRsOutBytes = kRsMaxK * 24;
+constexpr int kRsWarpSmem = 2 * kRsInBytes + kRsOutBytes;
+constexpr int kResampleSmem = kRsWarps * kRsWarpSmem;
+constexpr int kResampleCtasPerSm = 3;
+static_assert(kRsInBytes % 16 == 0 && kRsOutBytes % 16 == 0, "16-byte aligned staging buffers");
 
 __device__ __forceinline__ double warp_scan_inclusive(double v, const int lane) {
 #pragma unroll
@@ -306,69 +316,204 @@ __device__ __forceinline__ double warp_scan_inclusive(double v, const int lane) 
     }
     return v;
 }
-
-__global__ void __launch_bounds__(kResampleThreads)
-k_resample(const double* __restrict__ xyz, const int64_t* __restrict__ offsets, const int64_t S, const int K,
-           double* __restrict__ nodes) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warps_total = (int64_t)gridDim.x * (kResampleThreads / 32);
-    const double nan = __longlong_as_double(0x7ff8000000000000LL);
-    for (int64_t s = (int64_t)blockIdx.x * (kResampleThreads / 32) + (threadIdx.x >> 5); s < S; s += warps_total) {
-        const int64_t o0 = __ldg(offsets + s);
-        const int64_t n = __ldg(offsets + s + 1) - o0;
-        const double* p = xyz + 3 * o0;
-        double* dst = nodes + (int64_t)s * K * 3;
-        // ---- pass 1: total length (lane partial sums, one tree at the end).  It only has to be CLOSE to the
-        //      last cumulative length of pass 2: the nodes 0..K-2 lie at k L/(K-1) <= L (1 - 1/(K-1)).
-        double part = 0.0;
-        for (int64_t i = lane; i < n - 1; i += 32) {
-            const double dx = p[3 * i + 3] - p[3 * i], dy = p[3 * i + 4] - p[3 * i + 1], dz = p[3 * i + 5] - p[3 * i + 2];
-            part += sqrt_fast((dx * dx + dy * dy) + dz * dz);
-        }
+__device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-        const double L = part;
-        if (!(L > 0.0) || !(L < __longlong_as_double(0x7ff0000000000000LL))) {
-            // no point: NaN; zero length (or a single point): every node is the first point; non-finite length: NaN
-            const bool first = n > 0 && L == 0.0;
-            const double x = first ? p[0] : nan, y = first ? p[1] : nan, z = first ? p[2] : nan;
-            for (int k = lane; k < K; k += 32) { dst[3 * k] = x; dst[3 * k + 1] = y; dst[3 * k + 2] = z; }
-            continue;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint64_t policy) {
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(policy) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+// first node index k in [0, K-1] with k * step >= c (the product with 1/step is only a guess, off by one at most)
+__device__ __forceinline__ int first_node_at(const double c, const double step, const double inv_step, const int K) {
+    int k = __double2int_ru(c * inv_step);
+    if ((double)(k - 1) * step >= c) --k;
+    if ((double)k * step < c) ++k;
+    return min(max(k, 0), K - 1);
+}
+
+// no usable length: an empty polyline or a non-finite length -> NaN nodes; zero length (or a single point) -> the first point
+__device__ __forceinline__ void resample_degenerate(const double* __restrict__ p, const int64_t n, const double L, const int K,
+                                                    double* __restrict__ dst, const int lane) {
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    const bool first = n > 0 && L == 0.0;
+    const double x = first ? p[0] : nan, y = first ? p[1] : nan, z = first ? p[2] : nan;
+    for (int k = lane; k < K; k += 32) { dst[3 * k] = x; dst[3 * k + 1] = y; dst[3 * k + 2] = z; }
+}
+
+// Nodes of the segment [c0, c1) that starts at a with direction d: node k lies at arc length k * step.
+// `out` is the polyline's node table (shared or global memory).
+__device__ __forceinline__ void resample_emit(const double c0, const double c1, const double step, const double inv_step, const int K,
+                                              const double ax, const double ay, const double az,
+                                              const double dx, const double dy, const double dz, double* __restrict__ out) {
+    // first node index with k * step >= c0 (the product is only a guess: settle it with exact comparisons)
+    int k = min(max(__double2int_ru(c0 * inv_step), 0), K);
+    while (k > 0 && (double)(k - 1) * step >= c0) --k;
+    while (k < K - 1 && (double)k * step < c0) ++k;
+    const double inv = rcp_fast(c1 - c0);
+    for (; k < K - 1; ++k) {
+        const double t = (double)k * step;
+        if (!(t < c1)) break;
+        const double r = fmin(fmax((t - c0) * inv, 0.0), 1.0);
+        out[3 * k] = ax + r * dx; out[3 * k + 1] = ay + r * dy; out[3 * k + 2] = az + r * dz;
+    }
+}
+
+// any length, any K: points read from global memory twice (the second pass hits L1/L2), nodes stored directly
+__device__ __noinline__ void resample_generic(const double* __restrict__ p, const int64_t n, const int K, double* __restrict__ dst, const int lane) {
+    double part = 0.0;
+    for (int64_t i = lane; i < n - 1; i += 32) {
+        const double dx = p[3 * i + 3] - p[3 * i], dy = p[3 * i + 4] - p[3 * i + 1], dz = p[3 * i + 5] - p[3 * i + 2];
+        part += sqrt_fast((dx * dx + dy * dy) + dz * dz);
+    }
+    const double L = warp_sum(part);
+    if (!(L > 0.0) || !(L < __longlong_as_double(0x7ff0000000000000LL))) { resample_degenerate(p, n, L, K, dst, lane); return; }
+    const double step = L / (double)(K - 1);
+    const double inv_step = (double)(K - 1) / L;
+    double carry = 0.0;
+    for (int64_t base = 0; base < n - 1; base += 32) {
+        const int64_t i = base + lane;
+        double seg = 0.0, ax = 0.0, ay = 0.0, az = 0.0, dx = 0.0, dy = 0.0, dz = 0.0;
+        if (i < n - 1) {
+            ax = p[3 * i]; ay = p[3 * i + 1]; az = p[3 * i + 2];
+            dx = p[3 * i + 3] - ax; dy = p[3 * i + 4] - ay; dz = p[3 * i + 5] - az;
+            seg = sqrt_fast((dx * dx + dy * dy) + dz * dz);
         }
-        const double step = L / (double)(K - 1);
-        const double inv_step = (double)(K - 1) / L;
-        // ---- pass 2: emit
-        double carry = 0.0;
-        for (int64_t base = 0; base < n - 1; base += 32) {
-            const int64_t i = base + lane;
-            double seg = 0.0, ax = 0.0, ay = 0.0, az = 0.0, dx = 0.0, dy = 0.0, dz = 0.0;
-            if (i < n - 1) {
-                ax = p[3 * i]; ay = p[3 * i + 1]; az = p[3 * i + 2];
-                dx = p[3 * i + 3] - ax; dy = p[3 * i + 4] - ay; dz = p[3 * i + 5] - az;
-                seg = sqrt_fast((dx * dx + dy * dy) + dz * dz);
+        const double c1 = carry + warp_scan_inclusive(seg, lane);
+        double c0 = __shfl_up_sync(0xffffffffu, c1, 1);
+        if (lane == 0) c0 = carry;
+        carry = __shfl_sync(0xffffffffu, c1, 31);
+        if (i < n - 1 && c1 > c0) resample_emit(c0, c1, step, inv_step, K, ax, ay, az, dx, dy, dz, dst);
+    }
+    if (lane == 0) {                                               // the last node is the last point itself
+        dst[3 * (K - 1)] = p[3 * (n - 1)]; dst[3 * (K - 1) + 1] = p[3 * (n - 1) + 1]; dst[3 * (K - 1) + 2] = p[3 * (n - 1) + 2];
+    }
+}
+
+// Persistent grid, every warp walks polylines s, s + W, s + 2W, ...  The points of polyline s + W are in flight
+// (cp.async, whole 16-byte pieces, 2 buffers per warp) while polyline s is resampled out of shared memory; the
+// nodes are assembled in shared memory and leave as coalesced 16-byte stores.  Lane l owns segment 32 c + l of
+// chunk c; the cumulative length c1 at the end of a segment is the start of the next lane's, and the node range
+// of a segment is [first_node_at(c0), first_node_at(c1)): the boundary index is computed once and shuffled, so
+// every node is written exactly once.  [xyz_lo, xyz_hi) = bytes of the point array: a polyline whose 16-byte
+// pieces would cross them takes the generic path, like the ones too long for the buffers.
+__global__ void __launch_bounds__(kResampleThreads, kResampleCtasPerSm)
+k_resample(const double* __restrict__ xyz, const uint64_t xyz_lo, const uint64_t xyz_hi, const int64_t* __restrict__ offsets,
+           const int64_t S, const int K, double* __restrict__ nodes) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned char* wsm = smem + warp * kRsWarpSmem;
+    double* pout = (double*)(wsm + 2 * kRsInBytes);
+    const uint32_t in_u32 = smem_u32(wsm);
+    const uint64_t l2_stream = policy_evict_first();
+    const int64_t W = (int64_t)gridDim.x * kRsWarps;
+    const bool k_fits = K <= kRsMaxK;
+    const double inv_km1 = 1.0 / (double)(K - 1);
+
+    // stage polyline (o, n) into buffer b; returns the byte skew of its first point inside the buffer, or -1 if not staged
+    auto stage = [&](const int64_t o, const int64_t n, const int b) -> int {
+        if (!k_fits || n < 2 || n > kRsMaxN) return -1;
+        const uint64_t base = (uint64_t)(uintptr_t)(xyz + 3 * o);
+        const uint64_t a0 = base & ~(uint64_t)15;
+        const int skew = (int)(base - a0);
+        const int bytes = (skew + 24 * (int)n + 15) & ~15;
+        if (a0 < xyz_lo || a0 + (uint64_t)bytes > xyz_hi) return -1;
+        const uint32_t dst = in_u32 + b * kRsInBytes;
+        for (int j = lane * 16; j < bytes; j += 512) cp_async16(dst + j, (const unsigned char*)(uintptr_t)a0 + j, l2_stream);
+        return skew;
+    };
+
+    int64_t s = (int64_t)blockIdx.x * kRsWarps + warp;
+    int64_t o_cur = 0, n_cur = 0, o_nxt = 0, n_nxt = 0;
+    if (s < S) { o_cur = __ldg(offsets + s); n_cur = __ldg(offsets + s + 1) - o_cur; }
+    if (s + W < S) { o_nxt = __ldg(offsets + s + W); n_nxt = __ldg(offsets + s + W + 1) - o_nxt; }
+    int skew_cur = (s < S) ? stage(o_cur, n_cur, 0) : -1;
+    cp_async_commit();
+    int buf = 0;
+    for (; s < S; s += W) {
+        // offsets of the polyline after next: in flight during this iteration
+        int64_t o_nn = 0, n_nn = 0;
+        if (s + 2 * W < S) { o_nn = __ldg(offsets + s + 2 * W); n_nn = __ldg(offsets + s + 2 * W + 1) - o_nn; }
+        const int skew_nxt = (s + W < S) ? stage(o_nxt, n_nxt, buf ^ 1) : -1;
+        cp_async_commit();
+        cp_async_wait<1>();
+        __syncwarp();
+        const int n = (int)n_cur;
+        double* dst = nodes + s * K * 3;
+        if (skew_cur < 0) {
+            const double* p = xyz + 3 * o_cur;
+            if (n_cur <= 0) resample_degenerate(p, n_cur, 0.0, K, dst, lane);
+            else resample_generic(p, n_cur, K, dst, lane);
+        } else {
+            const double* pin = (const double*)(wsm + buf * kRsInBytes + skew_cur);
+            // ---- pass 1: segment lengths (kept in registers) and their total
+            double seg[4];
+            double part = 0.0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int i = 32 * c + lane;
+                seg[c] = 0.0;
+                if (i < n - 1) {
+                    const double dx = pin[3 * i + 3] - pin[3 * i], dy = pin[3 * i + 4] - pin[3 * i + 1], dz = pin[3 * i + 5] - pin[3 * i + 2];
+                    seg[c] = sqrt_fast((dx * dx + dy * dy) + dz * dz);
+                    part += seg[c];
+                }
             }
-            const double c1 = carry + warp_scan_inclusive(seg, lane);
-            double c0 = __shfl_up_sync(0xffffffffu, c1, 1);
-            if (lane == 0) c0 = carry;
-            carry = __shfl_sync(0xffffffffu, c1, 31);
-            if (i < n - 1 && c1 > c0) {
-                // first node index with k * step >= c0 (the product is only a guess: settle it with exact comparisons)
-                int k = min(max(__double2int_ru(c0 * inv_step), 0), K);
-                while (k > 0 && (double)(k - 1) * step >= c0) --k;
-                while (k < K - 1 && (double)k * step < c0) ++k;
-                const double inv = rcp_fast(c1 - c0);
-                for (; k < K - 1; ++k) {
-                    const double t = (double)k * step;
-                    if (!(t < c1)) break;
-                    const double r = fmin(fmax((t - c0) * inv, 0.0), 1.0);
-                    dst[3 * k] = ax + r * dx; dst[3 * k + 1] = ay + r * dy; dst[3 * k + 2] = az + r * dz;
+            const double L = warp_sum(part);
+            if (!(L > 0.0) || !(L < __longlong_as_double(0x7ff0000000000000LL))) {
+                resample_degenerate(pin, n, L, K, dst, lane);
+            } else {
+                const double step = L * inv_km1;
+                const double inv_step = rcp_fast(step);
+                // ---- pass 2: cumulative lengths, nodes into shared memory
+                double carry = 0.0;
+                int k_carry = 0;                                           // first node of the chunk's first segment
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (32 * c < n - 1) {                                  // warp-uniform
+                        const int i = 32 * c + lane;
+                        const double c1 = carry + warp_scan_inclusive(seg[c], lane);
+                        carry = __shfl_sync(0xffffffffu, c1, 31);
+                        const int k1 = first_node_at(c1, step, inv_step, K);      // end of this segment's node range ...
+                        int k0 = __shfl_up_sync(0xffffffffu, k1, 1);             // ... = start of the next lane's
+                        if (lane == 0) k0 = k_carry;
+                        k_carry = __shfl_sync(0xffffffffu, k1, 31);
+                        if (i < n - 1 && k0 < k1) {
+                            const double ax = pin[3 * i], ay = pin[3 * i + 1], az = pin[3 * i + 2];
+                            const double dx = pin[3 * i + 3] - ax, dy = pin[3 * i + 4] - ay, dz = pin[3 * i + 5] - az;
+                            const double c0 = c1 - seg[c];
+                            const double inv = rcp_fast(seg[c]);
+                            for (int k = k0; k < k1; ++k) {
+                                const double r = fmin(fmax(((double)k * step - c0) * inv, 0.0), 1.0);
+                                pout[3 * k] = ax + r * dx; pout[3 * k + 1] = ay + r * dy; pout[3 * k + 2] = az + r * dz;
+                            }
+                        }
+                    }
+                }
+                // nodes the rounding of the last cumulative length may have left out, and the last node: the last point itself
+                {
+                    const double* e = pin + 3 * (n - 1);
+                    for (int k = k_carry + lane; k < K; k += 32) { pout[3 * k] = e[0]; pout[3 * k + 1] = e[1]; pout[3 * k + 2] = e[2]; }
+                }
+                __syncwarp();
+                if ((K & 1) == 0) {                                        // 24 K bytes per polyline: 16-byte aligned rows
+                    const double2* src2 = (const double2*)pout;
+                    double2* dst2 = (double2*)dst;
+                    for (int j = lane; j < (3 * K) / 2; j += 32) dst2[j] = src2[j];
+                } else {
+                    for (int j = lane; j < 3 * K; j += 32) dst[j] = pout[j];
                 }
             }
         }
-        if (lane == 0) {                                           // the last node is the last point itself
-            dst[3 * (K - 1)] = p[3 * (n - 1)]; dst[3 * (K - 1) + 1] = p[3 * (n - 1) + 1]; dst[3 * (K - 1) + 2] = p[3 * (n - 1) + 2];
-        }
+        __syncwarp();                                                      // buffer `buf` and pout are free again
+        o_cur = o_nxt; n_cur = n_nxt; skew_cur = skew_nxt;
+        o_nxt = o_nn; n_nxt = n_nn;
+        buf ^= 1;
     }
+    cp_async_wait<0>();
 }
 
 }  // namespace tg
@@ -434,7 +579,7 @@ struct tg_context {
     DevBuf d_xyz64;                            // float64 copy of float32 input
     cudaStream_t s_copy = nullptr, s_back = nullptr;   // H2D / D2H streams of the chunked host path
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_comp[2] = {nullptr, nullptr};
-    bool grouped_ready = false;
+    bool grouped_ready = false, resample_ready = false;
     // bundle-reduce scratch
     PinBuf h_tiles;                   // TileDesc[nt] followed by int64 tile_first[B+1]
     DevBuf d_tiles, d_tsum, d_tcnt, d_tspread;
@@ -758,10 +903,15 @@ int tg_resample_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const i
         d_xyz = c->d_xyz64.p;
     }
     if (((uintptr_t)d_xyz & 7u) != 0) return set_err(TG_E_INVALID, "xyz must be 8-byte aligned");
-    const int64_t warps_per_cta = tg::kResampleThreads / 32;
-    const int64_t want = (S + warps_per_cta - 1) / warps_per_cta;
-    const int64_t cap = (int64_t)c->sm_count * (2048 / tg::kResampleThreads);
-    tg::k_resample<<<(unsigned)(want < cap ? want : cap), tg::kResampleThreads, 0, st>>>((const double*)d_xyz, d_offsets, S, n_nodes, d_nodes);
+    if (!c->resample_ready) {
+        TG_CUDA(cudaFuncSetAttribute(tg::k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::kResampleSmem));
+        c->resample_ready = true;
+    }
+    const int64_t want = ((S + tg::kRsBatch - 1) / tg::kRsBatch + tg::kRsWarps - 1) / tg::kRsWarps;
+    const int64_t cap = (int64_t)c->sm_count * tg::kResampleCtasPerSm;
+    const uint64_t lo = (uint64_t)(uintptr_t)d_xyz;
+    tg::k_resample<<<(unsigned)(want < cap ? want : cap), tg::kResampleThreads, tg::kResampleSmem, st>>>(
+        (const double*)d_xyz, lo, lo + 24ull * (uint64_t)P, d_offsets, S, n_nodes, d_nodes);
     c->launches += 1;
     TG_CUDA(cudaGetLastError());
     return TG_OK;
