@@ -126,4 +126,14 @@ def test_product_code_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f), errors="replace").read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
-                assert "reference_runner" not in src and "streamline_oracle" not in src, f
+                assert "reference_runner" not in src and "streamline_oracle" not in src and "resample_oracle" not in src, f
+
+
+def test_new_entry_points_reject_a_null_context_without_touching_cuda():
+    """ABI v2 additions validate their arguments before any CUDA call (runs on a box with no GPU)."""
+    lib = _lib.load()
+    assert lib.tg_bundle_spread_dev(None, None, None, None, 0, None, 0, None, None, None, None) == -1
+    assert lib.tg_metrics_csr_host_ex(None, None, 0, None, 0, 0, None, 0, None, None, None, None, None) == -1
+    assert lib.tg_resample_csr_dev(None, None, 0, None, 0, 0, 100, None, None) == -1
+    assert lib.tg_resample_csr_host(None, None, 0, None, 0, 0, 100, None) == -1
+    assert b"null context" in lib.tg_last_error()

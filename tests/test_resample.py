@@ -84,6 +84,25 @@ def test_gpu_resample_matches_oracle(gpu_ctx):
 
 
 @pytest.mark.gpu
+def test_gpu_resample_argument_checks_and_long_lines(gpu_ctx):
+    from lesion_condition_vae_b200 import _lib
+    pts, off = synth.random_walk_csr(np.array([5, 130, 129, 1000, 4097, 2, 1]), seed=8)
+    with pytest.raises(_lib.TractGeomError):
+        gpu_ctx.resample_host(pts, off, 1)                        # fewer than 2 nodes
+    with pytest.raises(_lib.TractGeomError):
+        gpu_ctx.resample_host(pts, off[::-1].copy(), 10)          # decreasing offsets
+    assert gpu_ctx.resample_host(pts[:0], np.zeros(1, np.int64), 10).shape == (0, 10, 3)
+    for K in (100, 128, 129, 1000):                                # beyond 128 nodes / 129 points: the generic path
+        got = gpu_ctx.resample_host(pts, off, K)
+        np.testing.assert_allclose(got, ro.resample_csr(pts, off, K), rtol=0, atol=1e-9 * np.abs(pts).max())
+    # an unaligned view of the point array (8 bytes off a 16-byte boundary) and its aligned copy agree bit for bit
+    raw = np.zeros(pts.size + 1)
+    view = raw[1:].reshape(-1, 3)
+    view[:] = pts
+    assert np.array_equal(gpu_ctx.resample_host(view, off, 100), gpu_ctx.resample_host(pts, off, 100))
+
+
+@pytest.mark.gpu
 def test_gpu_resample_properties_at_scale(gpu_ctx):
     """200k polylines on the device (sizes the oracle cannot cover): equal arc-length spacing, nodes on the
     polyline, end points exact, rigid-motion equivariance; a subsample against the oracle."""
