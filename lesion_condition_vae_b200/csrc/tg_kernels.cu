@@ -300,13 +300,12 @@ constexpr int kRsWarps = 8;
 constexpr int kResampleThreads = kRsWarps * 32;
 constexpr int kRsBatch = 1;                               // polylines per warp iteration
 constexpr int kRsMaxN = 129;                              // staged path: polylines of up to 129 points (4 chunks of 32 segments)
-constexpr int kRsMaxK = 128;                              // ... resampled to at most 128 nodes
 constexpr int kRsInBytes = ((kRsMaxN * 24 + 8 + 15) / 16) * 16 + 16;   // 8 bytes of skew in front, whole 16-byte pieces
-constexpr int kRsOutBytes = kRsMaxK * 24;
-constexpr int kRsWarpSmem = 2 * kRsInBytes + kRsOutBytes;
+constexpr int kRsCumBytes = ((kRsMaxN * 8 + 15) / 16) * 16;            // cumulative length at every point
+constexpr int kRsWarpSmem = 2 * kRsInBytes + kRsCumBytes;
 constexpr int kResampleSmem = kRsWarps * kRsWarpSmem;
 constexpr int kResampleCtasPerSm = 3;
-static_assert(kRsInBytes % 16 == 0 && kRsOutBytes % 16 == 0, "16-byte aligned staging buffers");
+static_assert(kRsInBytes % 16 == 0 && kRsCumBytes % 16 == 0, "16-byte aligned staging buffers");
 
 __device__ __forceinline__ double warp_scan_inclusive(double v, const int lane) {
 #pragma unroll
@@ -394,28 +393,30 @@ __device__ __noinline__ void resample_generic(const double* __restrict__ p, cons
 }
 
 // Persistent grid, every warp walks polylines s, s + W, s + 2W, ...  The points of polyline s + W are in flight
-// (cp.async, whole 16-byte pieces, 2 buffers per warp) while polyline s is resampled out of shared memory; the
-// nodes are assembled in shared memory and leave as coalesced 16-byte stores.  Lane l owns segment 32 c + l of
-// chunk c; the cumulative length c1 at the end of a segment is the start of the next lane's, and the node range
-// of a segment is [first_node_at(c0), first_node_at(c1)): the boundary index is computed once and shuffled, so
-// every node is written exactly once.  [xyz_lo, xyz_hi) = bytes of the point array: a polyline whose 16-byte
-// pieces would cross them takes the generic path, like the ones too long for the buffers.
+// (cp.async, whole 16-byte pieces, 2 buffers per warp) while polyline s is resampled out of shared memory.
+//   pass 1 (segment-parallel): lane l owns segment 32 c + l of chunk c; a warp scan per chunk leaves the
+//           cumulative length at every point in shared memory;
+//   pass 2 (node-parallel):    lane l owns node 32 r + l of round r: a branch-free binary search finds the last
+//           point whose cumulative length is <= the node's arc length (the segment then has positive length),
+//           the node is interpolated and stored — 3 x 8-byte stores per lane, 768 contiguous bytes per warp.
+// No lane-divergent loops, and every node has exactly one owner by construction.
+// [xyz_lo, xyz_hi) = bytes of the point array: a polyline whose 16-byte pieces would cross them takes the
+// generic path, like the ones too long for the buffers.
 __global__ void __launch_bounds__(kResampleThreads, kResampleCtasPerSm)
 k_resample(const double* __restrict__ xyz, const uint64_t xyz_lo, const uint64_t xyz_hi, const int64_t* __restrict__ offsets,
            const int64_t S, const int K, double* __restrict__ nodes) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned char* wsm = smem + warp * kRsWarpSmem;
-    double* pout = (double*)(wsm + 2 * kRsInBytes);
+    double* cum = (double*)(wsm + 2 * kRsInBytes);
     const uint32_t in_u32 = smem_u32(wsm);
     const uint64_t l2_stream = policy_evict_first();
     const int64_t W = (int64_t)gridDim.x * kRsWarps;
-    const bool k_fits = K <= kRsMaxK;
     const double inv_km1 = 1.0 / (double)(K - 1);
 
     // stage polyline (o, n) into buffer b; returns the byte skew of its first point inside the buffer, or -1 if not staged
     auto stage = [&](const int64_t o, const int64_t n, const int b) -> int {
-        if (!k_fits || n < 2 || n > kRsMaxN) return -1;
+        if (n < 2 || n > kRsMaxN) return -1;
         const uint64_t base = (uint64_t)(uintptr_t)(xyz + 3 * o);
         const uint64_t a0 = base & ~(uint64_t)15;
         const int skew = (int)(base - a0);
@@ -449,66 +450,52 @@ k_resample(const double* __restrict__ xyz, const uint64_t xyz_lo, const uint64_t
             else resample_generic(p, n_cur, K, dst, lane);
         } else {
             const double* pin = (const double*)(wsm + buf * kRsInBytes + skew_cur);
-            // ---- pass 1: segment lengths (kept in registers) and their total
-            double seg[4];
-            double part = 0.0;
+            // ---- pass 1: cumulative length at every point
+            double carry = 0.0;
+            if (lane == 0) cum[0] = 0.0;
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const int i = 32 * c + lane;
-                seg[c] = 0.0;
-                if (i < n - 1) {
-                    const double dx = pin[3 * i + 3] - pin[3 * i], dy = pin[3 * i + 4] - pin[3 * i + 1], dz = pin[3 * i + 5] - pin[3 * i + 2];
-                    seg[c] = sqrt_fast((dx * dx + dy * dy) + dz * dz);
-                    part += seg[c];
+                if (32 * c < n - 1) {                                      // warp-uniform
+                    const int i = 32 * c + lane;
+                    double seg = 0.0;
+                    if (i < n - 1) {
+                        const double dx = pin[3 * i + 3] - pin[3 * i], dy = pin[3 * i + 4] - pin[3 * i + 1], dz = pin[3 * i + 5] - pin[3 * i + 2];
+                        seg = sqrt_fast((dx * dx + dy * dy) + dz * dz);
+                    }
+                    const double c1 = carry + warp_scan_inclusive(seg, lane);
+                    if (i < n - 1) cum[i + 1] = c1;
+                    carry = __shfl_sync(0xffffffffu, c1, 31);
                 }
             }
-            const double L = warp_sum(part);
+            const double L = carry;
+            __syncwarp();
             if (!(L > 0.0) || !(L < __longlong_as_double(0x7ff0000000000000LL))) {
                 resample_degenerate(pin, n, L, K, dst, lane);
             } else {
                 const double step = L * inv_km1;
-                const double inv_step = rcp_fast(step);
-                // ---- pass 2: cumulative lengths, nodes into shared memory
-                double carry = 0.0;
-                int k_carry = 0;                                           // first node of the chunk's first segment
+                const int top = n - 2;                                     // last segment
+                // ---- pass 2: one node per lane and round
+                for (int k = lane; k < K; k += 32) {
+                    const double t = (double)k * step;
+                    int i = 0;                                             // last point with cum <= t, among 0 .. n-2
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    if (32 * c < n - 1) {                                  // warp-uniform
-                        const int i = 32 * c + lane;
-                        const double c1 = carry + warp_scan_inclusive(seg[c], lane);
-                        carry = __shfl_sync(0xffffffffu, c1, 31);
-                        const int k1 = first_node_at(c1, step, inv_step, K);      // end of this segment's node range ...
-                        int k0 = __shfl_up_sync(0xffffffffu, k1, 1);             // ... = start of the next lane's
-                        if (lane == 0) k0 = k_carry;
-                        k_carry = __shfl_sync(0xffffffffu, k1, 31);
-                        if (i < n - 1 && k0 < k1) {
-                            const double ax = pin[3 * i], ay = pin[3 * i + 1], az = pin[3 * i + 2];
-                            const double dx = pin[3 * i + 3] - ax, dy = pin[3 * i + 4] - ay, dz = pin[3 * i + 5] - az;
-                            const double c0 = c1 - seg[c];
-                            const double inv = rcp_fast(seg[c]);
-                            for (int k = k0; k < k1; ++k) {
-                                const double r = fmin(fmax(((double)k * step - c0) * inv, 0.0), 1.0);
-                                pout[3 * k] = ax + r * dx; pout[3 * k + 1] = ay + r * dy; pout[3 * k + 2] = az + r * dz;
-                            }
-                        }
+                    for (int h = 64; h > 0; h >>= 1) {
+                        const int j = i + h;
+                        const double cj = cum[min(j, top)];
+                        i = (j <= top && cj <= t) ? j : i;
                     }
-                }
-                // nodes the rounding of the last cumulative length may have left out, and the last node: the last point itself
-                {
-                    const double* e = pin + 3 * (n - 1);
-                    for (int k = k_carry + lane; k < K; k += 32) { pout[3 * k] = e[0]; pout[3 * k + 1] = e[1]; pout[3 * k + 2] = e[2]; }
-                }
-                __syncwarp();
-                if ((K & 1) == 0) {                                        // 24 K bytes per polyline: 16-byte aligned rows
-                    const double2* src2 = (const double2*)pout;
-                    double2* dst2 = (double2*)dst;
-                    for (int j = lane; j < (3 * K) / 2; j += 32) dst2[j] = src2[j];
-                } else {
-                    for (int j = lane; j < 3 * K; j += 32) dst[j] = pout[j];
+                    const double c0 = cum[i], c1 = cum[i + 1];
+                    const double ax = pin[3 * i], ay = pin[3 * i + 1], az = pin[3 * i + 2];
+                    const double bx = pin[3 * i + 3], by = pin[3 * i + 4], bz = pin[3 * i + 5];
+                    double r = fmin(fmax((t - c0) * rcp_fast(c1 - c0), 0.0), 1.0);
+                    const bool end = k == K - 1;                           // the last node is the last point itself
+                    const double ex = pin[3 * (n - 1)], ey = pin[3 * (n - 1) + 1], ez = pin[3 * (n - 1) + 2];
+                    const double x = end ? ex : ax + r * (bx - ax), y = end ? ey : ay + r * (by - ay), z = end ? ez : az + r * (bz - az);
+                    dst[3 * k] = x; dst[3 * k + 1] = y; dst[3 * k + 2] = z;
                 }
             }
         }
-        __syncwarp();                                                      // buffer `buf` and pout are free again
+        __syncwarp();                                                      // buffer `buf` and cum are free again
         o_cur = o_nxt; n_cur = n_nxt; skew_cur = skew_nxt;
         o_nxt = o_nn; n_nxt = n_nn;
         buf ^= 1;
