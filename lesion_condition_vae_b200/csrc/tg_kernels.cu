@@ -410,7 +410,7 @@ k_resample(const double* __restrict__ xyz, const uint64_t xyz_lo, const uint64_t
     unsigned char* wsm = smem + warp * kRsWarpSmem;
     double* cum = (double*)(wsm + 2 * kRsInBytes);
     const uint32_t in_u32 = smem_u32(wsm);
-    const uint64_t l2_stream = policy_evict_first();
+    const uint64_t l2_stream = policy_point_reads();
     const int64_t W = (int64_t)gridDim.x * kRsWarps;
     const double inv_km1 = 1.0 / (double)(K - 1);
 
