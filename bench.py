@@ -364,6 +364,11 @@ def run_ours(args):
                      "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": abytes,
                      "kernel": "k_metrics (17 metrics per polyline), avg CUDA-event time over the timed steps",
                      "frac_of_nominal_8TBs": achieved / 8000.0},
+        # the unit that actually binds the kernel: 96 fp64-pipe instructions per point (SASS of the
+        # steady block, profiles/r1_grouped_blocks.txt) against 60 lane-operations / clock / SM (tools/microbench.cu)
+        "fp64_pipe": {"lane_ops_per_point": 96, "achieved_tlaneops": 96 * P / (k_avg_max * 1e-3) / 1e12,
+                      "peak_tlaneops_at_max_clock": 60 * 148 * 1.965e9 / 1e12,
+                      "frac": 96 * P / (k_avg_max * 1e-3) / (60 * 148 * 1.965e9)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": 1e3 * e2e_sec / e2e_steps, "steps": e2e_steps},
         "e2e_f32_points": {"value": world * Se * e2e_steps / e2e32_sec, "unit": UNIT, "h2d_bytes_per_step": 12 * Pe + 8 * (Se + 1),
