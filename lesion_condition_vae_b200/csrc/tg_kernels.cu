@@ -291,14 +291,15 @@ k_spread_final(const int64_t* __restrict__ tile_first, const double* __restrict_
 // step that would feed /root/reference/src/vae/data_loader.py:94-100 (exactly 100 `point_id`s per
 // streamline; the reference ships no producer).  Node k lies at arc length k L/(K-1) on the polyline,
 // linearly interpolated inside its segment; node K-1 is the last point itself.
-// One WARP per polyline, two passes over its points (the second one hits L1/L2): pass 1 = total length,
-// pass 2 = every lane owns one segment [c0, c1) of the cumulative length and emits the nodes inside it.
-// c1 of lane i and c0 of lane i+1 are the SAME double (shuffled, never recomputed), so every node is
-// emitted exactly once.  HBM-bound: 24 n bytes read, 24 K bytes written per polyline.
+// One WARP per polyline.  Staged path (k_resample, up to 129 points): the points wait in shared memory, pass 1
+// is segment-parallel (cumulative lengths by warp scans), pass 2 node-parallel (binary search per node).
+// Generic path (resample_generic: longer polylines, or ones at the very edge of the point array): points read
+// from global memory twice, every lane owns one segment [c0, c1) per chunk and emits the nodes inside it;
+// c1 of lane i and c0 of lane i+1 are the SAME double (shuffled, never recomputed), so every node is emitted
+// exactly once.  Algorithmic traffic: 24 n bytes read, 24 K bytes written per polyline.
 // ------------------------------------------------------------------------------------------
 constexpr int kRsWarps = 8;
 constexpr int kResampleThreads = kRsWarps * 32;
-constexpr int kRsBatch = 1;                               // polylines per warp iteration
 constexpr int kRsMaxN = 129;                              // staged path: polylines of up to 129 points (4 chunks of 32 segments)
 constexpr int kRsInBytes = ((kRsMaxN * 24 + 8 + 15) / 16) * 16 + 16;   // 8 bytes of skew in front, whole 16-byte pieces
 constexpr int kRsCumBytes = ((kRsMaxN * 8 + 15) / 16) * 16;            // cumulative length at every point
@@ -323,17 +324,6 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint64_t policy) {
     asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "l"(policy) : "memory");
 }
-__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
-}
-// first node index k in [0, K-1] with k * step >= c (the product with 1/step is only a guess, off by one at most)
-__device__ __forceinline__ int first_node_at(const double c, const double step, const double inv_step, const int K) {
-    int k = __double2int_ru(c * inv_step);
-    if ((double)(k - 1) * step >= c) --k;
-    if ((double)k * step < c) ++k;
-    return min(max(k, 0), K - 1);
-}
-
 // no usable length: an empty polyline or a non-finite length -> NaN nodes; zero length (or a single point) -> the first point
 __device__ __forceinline__ void resample_degenerate(const double* __restrict__ p, const int64_t n, const double L, const int K,
                                                     double* __restrict__ dst, const int lane) {
@@ -894,7 +884,7 @@ int tg_resample_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const i
         TG_CUDA(cudaFuncSetAttribute(tg::k_resample, cudaFuncAttributeMaxDynamicSharedMemorySize, tg::kResampleSmem));
         c->resample_ready = true;
     }
-    const int64_t want = ((S + tg::kRsBatch - 1) / tg::kRsBatch + tg::kRsWarps - 1) / tg::kRsWarps;
+    const int64_t want = (S + tg::kRsWarps - 1) / tg::kRsWarps;
     const int64_t cap = (int64_t)c->sm_count * tg::kResampleCtasPerSm;
     const uint64_t lo = (uint64_t)(uintptr_t)d_xyz;
     tg::k_resample<<<(unsigned)(want < cap ? want : cap), tg::kResampleThreads, tg::kResampleSmem, st>>>(
