@@ -385,6 +385,53 @@ def test_heavy_tail_long_row_of_the_queue(gpu_ctx):
     assert_table_close(got, table.T, "long row vs long-polyline kernel")
 
 
+@pytest.mark.parametrize("law,S,seed", [("normal", 10_000_000, 5), ("heavy", 2_000_000, 4)])
+def test_full_size_configs(gpu_ctx, law, S, seed):
+    """BASELINE configs[4] (1e7 polylines, ~1e9 points, 24 GB) and configs[3] (2e6 polylines, heavy-tailed
+    lengths 10..5000) at their full sizes: counts exact; the length and
+    centroid columns of ALL polylines against torch.segment_reduce (independent of the oracle); the bundle
+    means against the column means; first / random / longest polylines against the oracle on all 17 columns."""
+    import torch
+    dev = torch.device("cuda:0")
+    if torch.cuda.get_device_properties(0).total_memory < 100e9:
+        pytest.skip("needs ~70 GB of device memory")
+    n = synth.torch_lengths(law, S, seed, dev)
+    pts, off = synth.torch_random_walk_csr(n, seed, dev)
+    P = pts.shape[0]
+    out = torch.empty((17, S), dtype=torch.float64, device=dev)
+    keep = torch.empty(S, dtype=torch.uint8, device=dev)
+    sums = torch.empty((1, 13), dtype=torch.float64, device=dev)
+    counts = torch.empty((1, 14), dtype=torch.int64, device=dev)
+    torch.cuda.synchronize()
+    gpu_ctx.metrics_dev(pts.data_ptr(), _lib.F64, off.data_ptr(), S, P, out.data_ptr(), keep.data_ptr())
+    gpu_ctx.bundle_reduce_dev(out.data_ptr(), keep.data_ptr(), 0, S, np.array([0, S]), sums.data_ptr(), counts.data_ptr())
+    gpu_ctx.synchronize()
+    assert int((keep == 3).sum()) == S and int(counts[0, 0]) == S and int(off[-1]) == P      # counts bit-exact
+    assert bool((counts[0, 1:] == S).all())
+    # length of every polyline: torch segmented sum of the segment norms (zero at the joints between polylines)
+    seg = torch.zeros(P, dtype=torch.float64, device=dev)
+    seg[:-1] = torch.linalg.norm(pts[1:] - pts[:-1], dim=1)
+    seg[off[1:] - 1] = 0.0
+    L = torch.segment_reduce(seg, "sum", lengths=n)
+    del seg
+    assert float(((out[0] - L).abs() / L).max()) < 1e-9
+    # centroid of every polyline, one coordinate at a time
+    for c in range(3):
+        cen = torch.segment_reduce(pts[:, c].contiguous(), "sum", lengths=n) / n
+        assert float((out[13 + c] - cen).abs().max()) < 1e-9
+    # bundle means = column means (deterministic tree on the device vs torch)
+    src = [0, 2, 4, 6, 7, 8, 10, 11, 12, 16, 13, 14, 15]
+    means = (sums[0] / counts[0, 1:]).cpu().numpy()
+    ref_means = out[src].mean(dim=1).cpu().numpy()
+    np.testing.assert_allclose(means, ref_means, rtol=1e-11, atol=1e-13)
+    # all 17 columns of a subsample against the oracle
+    idx = np.unique(np.concatenate([np.arange(300), np.random.default_rng(seed).integers(0, S, 300),
+                                    torch.topk(n, 20).indices.cpu().numpy(), torch.topk(-n, 20).indices.cpu().numpy()]))
+    off_h = off.cpu().numpy()
+    rows = [so.metrics_row(pts[off_h[s]:off_h[s + 1]].cpu().numpy()) for s in idx]
+    assert_table_close(out[:, torch.as_tensor(idx, device=dev)].T.cpu().numpy(), np.asarray(rows), f"{law} full-size subsample")
+
+
 def test_degenerate_grid_polylines(gpu_ctx):
     """Integer-grid polylines (duplicate points, collinear triples, right angles, reversals): almost every
     one leaves the speculative path and is recomputed by the exact pipeline; inf / NaN-to-number / zero
