@@ -388,7 +388,8 @@ def test_heavy_tail_long_row_of_the_queue(gpu_ctx):
 @pytest.mark.parametrize("law,S,seed", [("normal", 10_000_000, 5), ("heavy", 2_000_000, 4)])
 def test_full_size_configs(gpu_ctx, law, S, seed):
     """BASELINE configs[4] (1e7 polylines, ~1e9 points, 24 GB) and configs[3] (2e6 polylines, heavy-tailed
-    lengths 10..5000) at their full sizes: counts exact; the length and
+    lengths 10..5000) at their full sizes: counts exact; length, chord, tortuosity, straightness, bending
+    angle, bounding box, angular dispersion and
     centroid columns of ALL polylines against torch.segment_reduce (independent of the oracle); the bundle
     means against the column means; first / random / longest polylines against the oracle on all 17 columns."""
     import torch
@@ -419,6 +420,45 @@ def test_full_size_configs(gpu_ctx, law, S, seed):
     for c in range(3):
         cen = torch.segment_reduce(pts[:, c].contiguous(), "sum", lengths=n) / n
         assert float((out[13 + c] - cen).abs().max()) < 1e-9
+    # chord, tortuosity, straightness, bounding box of every polyline (ref:35-46, 114-117)
+    first, last = pts[off[:-1]], pts[off[1:] - 1]
+    chord = torch.sqrt(((last - first) ** 2).sum(dim=1))
+    assert float((out[1] - chord).abs().max()) < 1e-12
+    assert float((out[2] / (L / chord.clamp_min(1e-8)) - 1).abs().max()) < 1e-9
+    assert float((out[3] / (chord / L.clamp_min(1e-8)) - 1).abs().max()) < 1e-9
+    vol = torch.ones(S, dtype=torch.float64, device=dev)
+    for c in range(3):
+        col = pts[:, c].contiguous()
+        vol *= torch.segment_reduce(col, "max", lengths=n) - torch.segment_reduce(col, "min", lengths=n)
+        del col
+    assert float((out[9] / vol - 1).abs().max()) < 1e-12
+    del vol
+    # bending angle and angular dispersion of every polyline (ref:98-106, 143-148), re-derived with torch
+    d = pts[1:] - pts[:-1]
+    t = d / (torch.linalg.norm(d, dim=1, keepdim=True) + 1e-12)
+    del d
+    ang = torch.zeros(P, dtype=torch.float64, device=dev)
+    ang[:-2] = torch.acos(torch.clamp((t[:-1] * t[1:]).sum(dim=1), -1.0, 1.0))
+    joint = torch.zeros(P, dtype=torch.bool, device=dev)        # angle i uses points i, i+1, i+2: all three in one polyline
+    joint[off[1:] - 1] = True
+    joint[(off[1:] - 2).clamp_min(0)] = True
+    ang[joint] = 0.0
+    bend = torch.segment_reduce(ang, "sum", lengths=n) / (n - 2)
+    del ang
+    assert float((out[8] - bend).abs().max()) < 2e-9           # absolute: the mean angle is ~0.04 rad (ATOL of parity_rules)
+    tsq = torch.zeros(P, dtype=torch.float64, device=dev)
+    tsq[:-1] = (t * t).sum(dim=1)
+    tsq[off[1:] - 1] = 0.0
+    disp = torch.segment_reduce(tsq, "sum", lengths=n) / (n - 1)
+    del tsq
+    for c in range(3):
+        tc = torch.zeros(P, dtype=torch.float64, device=dev)
+        tc[:-1] = t[:, c]
+        tc[off[1:] - 1] = 0.0
+        disp -= (torch.segment_reduce(tc, "sum", lengths=n) / (n - 1)) ** 2
+        del tc
+    del t, joint
+    assert float((out[16] - disp).abs().max()) < 1e-12          # mean |t - tbar|^2 = mean |t|^2 - |tbar|^2
     # bundle means = column means (deterministic tree on the device vs torch)
     src = [0, 2, 4, 6, 7, 8, 10, 11, 12, 16, 13, 14, 15]
     means = (sums[0] / counts[0, 1:]).cpu().numpy()
