@@ -472,6 +472,81 @@ def test_full_size_configs(gpu_ctx, law, S, seed):
     assert_table_close(out[:, torch.as_tensor(idx, device=dev)].T.cpu().numpy(), np.asarray(rows), f"{law} full-size subsample")
 
 
+@pytest.mark.parametrize("law,S,seed", [("normal", 10_000_000, 5), ("heavy", 2_000_000, 4)])
+def test_full_size_curvature_torsion_eigen_columns(gpu_ctx, law, S, seed):
+    """The differential and spectral columns of EVERY polyline at the full BASELINE sizes, re-derived with torch
+    from the reference formulas (np.gradient with one-sided ends twice, cross product, ref:48-96; covariance
+    eigenvalues, ref:119-141) — no oracle involved."""
+    import torch
+    dev = torch.device("cuda:0")
+    if torch.cuda.get_device_properties(0).total_memory < 150e9:
+        pytest.skip("needs ~130 GB of device memory")
+    n = synth.torch_lengths(law, S, seed, dev)
+    pts, off = synth.torch_random_walk_csr(n, seed, dev)
+    P = pts.shape[0]
+    out = torch.empty((17, S), dtype=torch.float64, device=dev)
+    keep = torch.empty(S, dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+    gpu_ctx.metrics_dev(pts.data_ptr(), _lib.F64, off.data_ptr(), S, P, out.data_ptr(), keep.data_ptr())
+    gpu_ctx.synchronize()
+    assert int((keep == 3).sum()) == S
+    nf = n.to(torch.float64)
+
+    # np.gradient along each polyline: (f[next] - f[prev]) * s, next/prev clamped to the polyline, s = 1 at its ends
+    i = torch.arange(P, device=dev)
+    lo = torch.repeat_interleave(off[:-1], n)
+    hi = torch.repeat_interleave(off[1:] - 1, n)
+    prv = torch.maximum(i - 1, lo)
+    nxt = torch.minimum(i + 1, hi)
+    sc = torch.where((i == lo) | (i == hi), 1.0, 0.5).to(torch.float64)[:, None]
+    interior = i < hi                                             # j < n-1 (ref:82: left-point rule of the energy)
+    del i, lo, hi
+
+    def grad(f):
+        return (f[nxt] - f[prv]) * sc
+
+    v = grad(pts)
+    a = grad(v)
+    b = torch.linalg.cross(v, a)
+    del a
+    kappa = torch.linalg.norm(b, dim=1) / (torch.linalg.norm(v, dim=1) + 1e-12) ** 3          # ref:57-59
+    kmean = torch.segment_reduce(kappa, "sum", lengths=n) / nf
+    assert float(((out[4] - kmean).abs() / (1e-9 * kmean + 1e-13)).max()) <= 1.0
+    kvar = torch.segment_reduce((kappa - torch.repeat_interleave(kmean, n)) ** 2, "sum", lengths=n) / nf
+    assert float(((out[5] - kvar.sqrt()).abs() / (1e-9 * kvar.sqrt() + 1e-13)).max()) <= 1.0
+    ds = torch.zeros(P, dtype=torch.float64, device=dev)
+    ds[:-1] = torch.linalg.norm(pts[1:] - pts[:-1], dim=1) + 1e-12                            # ref:77
+    energy = torch.segment_reduce(torch.where(interior, kappa * kappa * ds, 0.0), "sum", lengths=n)
+    assert float(((out[6] - energy).abs() / (1e-9 * energy + 1e-13)).max()) <= 1.0
+    del kappa, ds, v, interior, kvar
+    db = grad(b)                                                                             # ref:91
+    tau = (b * db).sum(dim=1) / (torch.linalg.norm(b, dim=1) ** 2 + 1e-12)                    # ref:92-94
+    del b, db
+    tmean = torch.where(n >= 4, torch.segment_reduce(tau, "sum", lengths=n) / nf, 0.0)        # ref:86,96
+    # torsion is a sum that cancels: the parity rule for it is absolute (parity_rules.ATOL) plus 1e-9 of the terms' size
+    tabs = torch.segment_reduce(tau.abs(), "sum", lengths=n) / nf
+    assert float(((out[7] - tmean).abs() / (1e-9 * tabs + 1e-12)).max()) <= 1.0
+    del tau, tabs, prv, nxt, sc
+
+    # covariance eigenvalues (ddof = 1) about the centroid
+    C = torch.empty((S, 3, 3), dtype=torch.float64, device=dev)
+    cen = [torch.segment_reduce(pts[:, c].contiguous(), "sum", lengths=n) / nf for c in range(3)]
+    q = [pts[:, c] - torch.repeat_interleave(cen[c], n) for c in range(3)]
+    for r in range(3):
+        for c in range(r, 3):
+            C[:, r, c] = C[:, c, r] = torch.segment_reduce(q[r] * q[c], "sum", lengths=n) / (nf - 1)
+    del q
+    lam = torch.linalg.eigvalsh(C.cpu()).flip(1).to(dev)             # LAPACK on the host (descending): cuSOLVER's batched syev rejects this batch
+    l1, l2, l3 = lam[:, 0], lam[:, 1], lam[:, 2]
+    cond = l1 / l3
+    wide = torch.clamp(2e-14 * cond, min=1e-9)                                               # parity_rules: eigen ratios
+    ok = l3 > 1e-12
+    assert bool(ok.all())                                                                    # no inf ratios in these laws
+    assert float(((out[10] / (l1 / l2) - 1).abs() / wide).max()) <= 1.0
+    assert float(((out[11] / (l2 / l3) - 1).abs() / wide).max()) <= 1.0
+    assert float((out[12] / (l1 / (l1 + l2 + l3 + 1e-12)) - 1).abs().max()) <= 1e-9
+
+
 def test_degenerate_grid_polylines(gpu_ctx):
     """Integer-grid polylines (duplicate points, collinear triples, right angles, reversals): almost every
     one leaves the speculative path and is recomputed by the exact pipeline; inf / NaN-to-number / zero
