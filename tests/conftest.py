@@ -24,6 +24,17 @@ def built_library():
         print(f"[conftest] library build skipped: {e}")
 
 
+@pytest.fixture(autouse=True)
+def release_torch_cache(request):
+    """The library allocates with cudaMalloc, outside torch's caching allocator: hand the cache back after every
+    GPU test so a 100 GB full-size test cannot starve the next one."""
+    yield
+    if "gpu" in request.keywords:
+        import torch
+        if torch.cuda.is_available():
+            torch.cuda.empty_cache()
+
+
 @pytest.fixture(scope="session")
 def golden():
     import numpy as np
