@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 2   /* 2: + tg_bundle_spread_dev, tg_metrics_csr_host_ex, tg_resample_csr_* (version-1 entry points unchanged) */
+#define TG_ABI_VERSION 2   /* 2: + tg_bundle_spread_dev, tg_metrics_csr_host_ex, tg_resample_csr_*, host ingest helpers (version-1 entry points unchanged) */
 
 #define TG_N_METRICS 17
 enum tg_metric {                 /* tract_geom_proc.py:164-187 */
@@ -139,6 +139,17 @@ int tg_resample_csr_dev(tg_context* ctx, const void* d_xyz, int xyz_dtype, const
                         int64_t S, int64_t P, int n_nodes, double* d_nodes, void* stream);
 int tg_resample_csr_host(tg_context* ctx, const void* h_xyz, int xyz_dtype, const int64_t* h_offsets,
                          int64_t S, int64_t P, int n_nodes, double* h_nodes);
+
+/* Host-side ingest helpers for legacy VTK tract files (replace the Python `while` walk of
+ * tract_geom_proc.py:17-25 and the text parsing behind pv.read).  No device, no context needed.
+ *   tg_vtk_lines_to_csr: legacy cell array [n, i0..i(n-1), n, ...] of L ints -> CSR offsets (capacity L + 1)
+ *                        and connectivity (capacity L); TG_E_INVALID when a count is negative or overruns.
+ *   tg_parse_ascii_f64 / _i64: `want` whitespace-separated numbers from text[0, len) (inf / nan accepted for
+ *                        doubles); *consumed = bytes read; TG_E_INVALID when the text ends or is malformed. */
+int tg_vtk_lines_to_csr(const int64_t* lines, int64_t L, int64_t* offsets, int64_t* conn,
+                        int64_t* n_cells, int64_t* n_conn);
+int tg_parse_ascii_f64(const char* text, int64_t len, int64_t want, double* out, int64_t* consumed);
+int tg_parse_ascii_i64(const char* text, int64_t len, int64_t want, int64_t* out, int64_t* consumed);
 
 /* Introspection for bench.py / tests: kernels launched by this context since creation. */
 int tg_launch_count(tg_context* ctx, int64_t* launches);

@@ -20,6 +20,7 @@ EXPORTS = (
     "tg_stream", "tg_host_alloc", "tg_host_free", "tg_metrics_csr_dev", "tg_bundle_reduce_dev",
     "tg_metrics_csr_host", "tg_launch_count", "tg_bundle_spread_dev", "tg_metrics_csr_host_ex",
     "tg_resample_csr_dev", "tg_resample_csr_host",
+    "tg_vtk_lines_to_csr", "tg_parse_ascii_f64", "tg_parse_ascii_i64",
 )
 
 
@@ -59,6 +60,9 @@ def load():
     lib.tg_bundle_spread_dev.argtypes = [vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp]
     lib.tg_resample_csr_dev.argtypes = [vp, vp, i32, vp, i64, i64, i32, vp, vp]
     lib.tg_resample_csr_host.argtypes = [vp, vp, i32, vp, i64, i64, i32, vp]
+    lib.tg_vtk_lines_to_csr.argtypes = [vp, i64, vp, vp, C.POINTER(i64), C.POINTER(i64)]
+    lib.tg_parse_ascii_f64.argtypes = [C.c_char_p, i64, i64, vp, C.POINTER(i64)]
+    lib.tg_parse_ascii_i64.argtypes = [C.c_char_p, i64, i64, vp, C.POINTER(i64)]
     lib.tg_metrics_csr_host_ex.argtypes = [vp, vp, i32, vp, i64, i64, vp, i64, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
@@ -189,6 +193,36 @@ class Context:
         check(self._lib.tg_metrics_csr_host(self._h, _ptr(points), code, _ptr(offsets), S, P, _ptr(bo), B,
                                             _ptr(out), _ptr(keep), _ptr(sums), _ptr(counts)))
         return out, keep, sums, counts
+
+
+# ---- host-side ingest helpers (no device needed) ----
+def vtk_lines_to_csr(lines):
+    """Legacy cell array -> (offsets int64[S+1], connectivity int64[C]); raises TractGeomError on a corrupt array."""
+    lib = load()
+    lines = np.ascontiguousarray(lines, dtype=np.int64)
+    L = lines.size
+    offsets = np.empty(L + 1, dtype=np.int64)
+    conn = np.empty(max(L, 1), dtype=np.int64)
+    ns, nc = C.c_int64(), C.c_int64()
+    check(lib.tg_vtk_lines_to_csr(_ptr(lines), L, _ptr(offsets), _ptr(conn), C.byref(ns), C.byref(nc)))
+    return offsets[:ns.value + 1].copy(), conn[:nc.value].copy()
+
+
+def parse_ascii(buf, start, count, integer=False):
+    """`count` whitespace-separated numbers of bytes object `buf` from byte `start` -> (array, bytes consumed)."""
+    lib = load()
+    out = np.empty(count, dtype=np.int64 if integer else np.float64)
+    used = C.c_int64()
+    view = memoryview(buf)[start:]
+    cbuf = (C.c_char * len(view)).from_buffer_copy(view) if not isinstance(buf, bytes) else None
+    fn = lib.tg_parse_ascii_i64 if integer else lib.tg_parse_ascii_f64
+    if cbuf is None:
+        # bytes: pass a pointer into the object itself (no copy of the remaining file)
+        addr = C.cast(C.c_char_p(buf), C.c_void_p).value + start
+        check(fn(C.cast(addr, C.c_char_p), len(buf) - start, count, _ptr(out), C.byref(used)))
+    else:
+        check(fn(cbuf, len(view), count, _ptr(out), C.byref(used)))
+    return out, used.value
 
 
 _default_ctx = {}

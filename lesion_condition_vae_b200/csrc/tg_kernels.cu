@@ -18,6 +18,7 @@
 #include <string>
 #include <vector>
 #include <algorithm>
+#include <charconv>
 
 namespace tg {
 
@@ -918,6 +919,66 @@ int tg_resample_csr_host(tg_context* c, const void* h_xyz, int xyz_dtype, const 
     if ((rc = tg_resample_csr_dev(c, c->d_xyz.p, xyz_dtype, (const int64_t*)c->d_off.p, S, P, n_nodes, (double*)c->d_nodes.p, st))) return rc;
     TG_CUDA(cudaMemcpyAsync(h_nodes, c->d_nodes.p, node_bytes, cudaMemcpyDeviceToHost, st));
     TG_CUDA(cudaStreamSynchronize(st));
+    return TG_OK;
+}
+
+// ---- host-side ingest helpers: no device, no context --------------------------------------
+int tg_vtk_lines_to_csr(const int64_t* lines, int64_t L, int64_t* offsets, int64_t* conn, int64_t* n_cells, int64_t* n_conn) {
+    if (L < 0 || (L > 0 && !lines) || !offsets || !n_cells || !n_conn || (L > 0 && !conn)) return set_err(TG_E_INVALID, "null argument");
+    int64_t i = 0, s = 0, c = 0;
+    offsets[0] = 0;
+    while (i < L) {
+        const int64_t n = lines[i];
+        if (n < 0 || n > L - i - 1) return set_err(TG_E_INVALID, "corrupt LINES array");
+        for (int64_t k = 0; k < n; ++k) conn[c + k] = lines[i + 1 + k];
+        c += n;
+        offsets[++s] = c;
+        i += 1 + n;
+    }
+    *n_cells = s;
+    *n_conn = c;
+    return TG_OK;
+}
+
+static inline const char* skip_space(const char* p, const char* end) {
+    while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r' || *p == '\f' || *p == '\v')) ++p;
+    return p;
+}
+
+int tg_parse_ascii_f64(const char* text, int64_t len, int64_t want, double* out, int64_t* consumed) {
+    if (len < 0 || want < 0 || (len > 0 && !text) || (want > 0 && !out) || !consumed) return set_err(TG_E_INVALID, "null argument");
+    const char* p = text;
+    const char* end = text + len;
+    for (int64_t k = 0; k < want; ++k) {
+        p = skip_space(p, end);
+        if (p < end && *p == '+') ++p;                                  // from_chars takes no leading plus
+        const std::from_chars_result r = std::from_chars(p, end, out[k]);
+        if (r.ec == std::errc::result_out_of_range) {                   // strtod semantics: +-inf / 0 with the token consumed
+            char tmp[64];
+            const size_t m = std::min<size_t>(sizeof tmp - 1, (size_t)(r.ptr - p));
+            memcpy(tmp, p, m); tmp[m] = 0;
+            out[k] = strtod(tmp, nullptr);
+        } else if (r.ec != std::errc()) {
+            return set_err(TG_E_INVALID, p >= end ? "truncated ASCII block" : "malformed number in ASCII block");
+        }
+        p = r.ptr;
+    }
+    *consumed = (int64_t)(p - text);
+    return TG_OK;
+}
+
+int tg_parse_ascii_i64(const char* text, int64_t len, int64_t want, int64_t* out, int64_t* consumed) {
+    if (len < 0 || want < 0 || (len > 0 && !text) || (want > 0 && !out) || !consumed) return set_err(TG_E_INVALID, "null argument");
+    const char* p = text;
+    const char* end = text + len;
+    for (int64_t k = 0; k < want; ++k) {
+        p = skip_space(p, end);
+        if (p < end && *p == '+') ++p;
+        const std::from_chars_result r = std::from_chars(p, end, out[k]);
+        if (r.ec != std::errc()) return set_err(TG_E_INVALID, p >= end ? "truncated ASCII block" : "malformed integer in ASCII block");
+        p = r.ptr;
+    }
+    *consumed = (int64_t)(p - text);
     return TG_OK;
 }
 

@@ -32,6 +32,24 @@ class VTKFormatError(ValueError):
     pass
 
 
+_NATIVE = False          # False: not probed yet; None: unavailable
+
+
+def _native():
+    """libtractgeom.so's host-side ingest helpers (tg_vtk_lines_to_csr, tg_parse_ascii_*), or None when the
+    library is not built: the numpy statements below then do the same work, slower.  File parsing only — the
+    metrics themselves have no CPU path."""
+    global _NATIVE
+    if _NATIVE is False:
+        try:
+            from . import _lib
+            _lib.load()
+            _NATIVE = _lib
+        except (ImportError, OSError, AttributeError):
+            _NATIVE = None
+    return _NATIVE
+
+
 class _Cursor:
     def __init__(self, buf: bytes):
         self.b = buf
@@ -68,6 +86,15 @@ class _Cursor:
     def ascii(self, dtype, count):
         if count == 0:
             return np.empty(0, dtype=np.dtype(dtype).newbyteorder("="))
+        native = _native()
+        if native is not None:
+            integer = np.dtype(dtype).kind != "f"
+            try:
+                vals, used = native.parse_ascii(self.b, self.i, count, integer=integer)
+            except native.TractGeomError as e:
+                raise VTKFormatError(str(e)) from e
+            self.i += used
+            return vals if integer else vals.astype(np.dtype(dtype).newbyteorder("="), copy=False)
         # split() is C speed; the remainder stays unparsed
         parts = self.b[self.i:].split(None, count)
         if len(parts) < count:
@@ -194,6 +221,12 @@ def legacy_lines_to_csr(lines, n_cells=None):
                 offsets = np.arange(n_cells + 1, dtype=np.int64) * n0
                 mask = np.ones(L, dtype=bool); mask[h] = False
                 return offsets, lines[mask]
+    native = _native()
+    if native is not None:
+        try:
+            return native.vtk_lines_to_csr(lines)
+        except native.TractGeomError as e:
+            raise VTKFormatError("corrupt LINES array") from e
     lst = lines.tolist() if L < (1 << 26) else None
     if lst is not None:
         while i < L:

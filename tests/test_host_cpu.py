@@ -76,6 +76,44 @@ def test_legacy_lines_walk_matches_reference_loop():
     assert off2.tolist() == [0, 2, 4, 6] and conn2.tolist() == [0, 1, 2, 3, 4, 5]
 
 
+def test_native_ingest_helpers_agree_with_the_numpy_statements(tmp_path, monkeypatch):
+    """vtk_io uses the library's host-side helpers when it is built and numpy otherwise: same arrays either way,
+    same errors on corrupt input (ASCII numbers incl. signs, exponents, inf / nan; ragged and empty cells)."""
+    assert vtk_io._native() is not None                          # the library is built in this checkout
+    rng = np.random.default_rng(7)
+    lines = []
+    for _ in range(300):
+        k = int(rng.integers(0, 9))
+        lines += [k] + rng.integers(0, 1000, k).tolist()
+    lines = np.asarray(lines, dtype=np.int64)
+    vals = np.concatenate([rng.normal(size=500) * 10.0 ** rng.integers(-30, 30, 500), [0.0, -0.0, np.inf, -np.inf, 1e-320, 1.7976931348623157e308]])
+    txt = " ".join(repr(float(v)) for v in vals).replace("e+", "E+").encode() + b" nan +2.5 -3 7\n 8"
+    pts, off = synth.config1(S=40, seed=2)
+    files = [vtk_io.write_polylines(tmp_path / f"f{i}.vtk", pts, off, binary=b, layout=l)
+             for i, (b, l) in enumerate([(False, "classic"), (False, "offsets"), (True, "classic")])]
+
+    def run():
+        f, used = vtk_io._Cursor(txt).ascii(">f8", len(vals) + 4), None
+        cur = vtk_io._Cursor(txt); cur.ascii(">f8", len(vals) + 2); ints = cur.ascii(">i4", 3)
+        return vtk_io.legacy_lines_to_csr(lines), f, ints, [vtk_io.read_polylines_csr(p) for p in files]
+
+    native = run()
+    monkeypatch.setattr(vtk_io, "_NATIVE", None)
+    plain = run()
+    assert np.array_equal(native[0][0], plain[0][0]) and np.array_equal(native[0][1], plain[0][1])
+    assert np.array_equal(native[1], plain[1], equal_nan=True) and np.array_equal(native[1][:len(vals)], vals)
+    assert native[2].tolist() == plain[2].tolist() == [-3, 7, 8]
+    assert native[1][len(vals) + 1:].tolist() == [2.5, -3.0, 7.0]
+    for (a, b), (c, d) in zip(native[3], plain[3]):
+        assert np.array_equal(a, c) and np.array_equal(b, d)
+    for mode in (False, None):                                   # native, then numpy
+        monkeypatch.setattr(vtk_io, "_NATIVE", mode)
+        with pytest.raises(vtk_io.VTKFormatError):
+            vtk_io.legacy_lines_to_csr(np.array([3, 0, 1], dtype=np.int64))          # count overruns the array
+        with pytest.raises(vtk_io.VTKFormatError):
+            vtk_io._Cursor(b"1 2 3").ascii(">f8", 4)                                  # truncated
+
+
 def test_prefix_rule():
     n = np.array([5, 2, 9, 0, 3, 3, 1, 4])
     assert tgp._prefix_for(n, 1) == 1
