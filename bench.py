@@ -63,6 +63,29 @@ def workload_name(S, law):
     return f"heavy-tailed tractogram, {S} polylines/GPU, n=min(5000,floor(10/U)) (BASELINE configs[3])"
 
 
+def bind_to_gpu_numa_node(local):
+    """One process per GPU: run on the cores of the NUMA node the GPU hangs off, so that the pinned host buffers of
+    the e2e leg are allocated next to it (cudaHostAlloc places pages by first touch).  Best effort; returns the node."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def algorithmic_bytes(P, S):
     """BASELINE.md §5 / SURVEY.md §8d."""
     return 24 * P + 8 * (S + 1) + 136 * S + S
@@ -204,6 +227,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; this path has no CPU implementation (use --impl reference for the CPU baseline)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None      # before any pinned allocation (first touch)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -355,7 +379,8 @@ def run_ours(args):
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(S, args.law), "streamlines_per_gpu": S, "points_per_gpu": P,
-                   "parallelism": f"csr-range shards x{world}" + (", NCCL all-gather of 27 bundle partials/rank" if world > 1 else ""),
+                   "parallelism": f"csr-range shards x{world}" + (", NCCL all-gather of 27 bundle partials/rank" if world > 1 else "")
+                   + (f", ranks bound to their GPU's NUMA node (rank 0: node {numa})" if numa is not None else ""),
                    "l2": "inputs (24 B/point, >> 126 MB L2) stream from HBM every step; no flush needed",
                    "e2e_workload": f"first {Se} polylines ({Pe} points) per GPU from pinned host buffers, full df_sl table copied back"},
         "points_per_sec": tot_P * args.steps / sec,
