@@ -21,7 +21,9 @@
  * All functions return 0 on success, a negative TG_E_* code on failure; tg_last_error() returns a
  * static thread-local message for the last failure.  Nothing here calls exit()/abort().
  * A context is bound to one CUDA device and is not thread-safe (the reference is single-threaded,
- * comprehensive_tract_geometry_analysis.py:169-195 calls it serially).
+ * comprehensive_tract_geometry_analysis.py:169-195 calls it serially).  Its device scratch (work queue,
+ * tile partials, float64 copy of float32 points) is shared by all calls: calls on ONE context must be
+ * stream-ordered with respect to each other — use one stream per context, or one context per stream.
  */
 #ifndef TRACTGEOM_H
 #define TRACTGEOM_H
