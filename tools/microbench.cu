@@ -83,6 +83,54 @@ void run(const char* name, double ops_per_iter_per_thread, int warps_per_sm, int
            per_s / nsm / clk_hz, clk_hz / 1e6);
 }
 
+// fp64 tensor-core MMA (DMMA m8n8k4: 256 FMA per warp instruction = 8 per lane): own pipe or the vector fp64 pipe?
+// MIX = 0: DMMA only; MIX = 1: one DFMA per DMMA beside it (8 + 1 lane-FMAs); MIX = 2: four DFMA per DMMA (8 + 4).
+template <int MIX>
+__global__ void __launch_bounds__(256) k_dmma(double* out, double seed, int iters) {
+    double c0[4], c1[4], f[4];
+    const double a = seed * 1.0000001, b = 1e-3 + threadIdx.x * 1e-9;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { c0[j] = seed + j; c1[j] = seed - j; f[j] = seed + 0.5 * j; }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+                         : "+d"(c0[j]), "+d"(c1[j]) : "d"(a), "d"(b));
+            if (MIX == 1) f[j] = fma(f[j], 1.0000001, 1e-9);
+            if (MIX == 2) {
+                f[0] = fma(f[0], 1.0000001, 1e-9); f[1] = fma(f[1], 1.0000001, 1e-9);
+                f[2] = fma(f[2], 1.0000001, 1e-9); f[3] = fma(f[3], 1.0000001, 1e-9);
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += c0[j] + c1[j] + f[j];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int MIX>
+void run_dmma(const char* name, int warps_per_sm, int nsm, double* d_out, double clk_hz) {
+    const int threads = 256, blocks = nsm * (warps_per_sm * 32 / threads);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    k_dmma<MIX><<<blocks, threads>>>(d_out, 1.0, ITERS);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 5; ++r) {
+        CK(cudaEventRecord(e0));
+        k_dmma<MIX><<<blocks, threads>>>(d_out, 1.0, ITERS);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms < best) best = ms;
+    }
+    const double lanes = (double)blocks * threads * ITERS * 4;              // DMMA issued per lane
+    const double mma_fma = 8.0 * lanes / (best * 1e-3), vec_fma = (MIX == 1 ? 1.0 : MIX == 2 ? 4.0 : 0.0) * lanes / (best * 1e-3);
+    printf("%-34s warps/SM=%2d  %8.3f ms  tensor %7.2f + vector %6.2f FMA lane-ops/clk/SM\n", name, warps_per_sm, best,
+           mma_fma / nsm / clk_hz, vec_fma / nsm / clk_hz);
+}
+
 __global__ void k_seed_accuracy(const double* x, double* rs, double* rc, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { rs[i] = mufu_rsqrt64(x[i]); rc[i] = mufu_rcp64(x[i]); }
@@ -121,6 +169,11 @@ int main() {
     run<DFMA_LDS>("DFMA + LDS.64 4:1 (count DFMA)", CH, 16, nsm, d_out, clk);
     run<MUFU64_ONLY>("MUFU.RSQ64H + DADD", CH, 16, nsm, d_out, clk);
     run<F2F_ONLY>("F2F f64->f32->f64 pair + FADD", CH, 16, nsm, d_out, clk);
+
+    run_dmma<0>("DMMA m8n8k4 only", 16, nsm, d_out, clk);
+    run_dmma<0>("DMMA m8n8k4 only", 8, nsm, d_out, clk);
+    run_dmma<1>("DMMA + 1 DFMA", 16, nsm, d_out, clk);
+    run_dmma<2>("DMMA + 4 DFMA", 16, nsm, d_out, clk);
 
     // seed accuracy
     const int N = 1 << 20;
