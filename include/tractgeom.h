@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 2   /* 2: + tg_bundle_spread_dev, tg_metrics_csr_host_ex, tg_resample_csr_*, host ingest helpers (version-1 entry points unchanged) */
+#define TG_ABI_VERSION 3   /* 2: + tg_bundle_spread_dev, tg_metrics_csr_host_ex, tg_resample_csr_*, host ingest helpers; 3: + tg_build_id (earlier entry points unchanged) */
 
 #define TG_N_METRICS 17
 enum tg_metric {                 /* tract_geom_proc.py:164-187 */
@@ -71,6 +71,9 @@ typedef struct tg_context tg_context;
 
 /* Library / device ------------------------------------------------------------------------- */
 int         tg_abi_version(void);
+/* Identity of the binary: sha256 prefix over the kernel sources, this header and the nvcc command line
+ * (lesion_condition_vae_b200/build.py::source_id).  Tests and bench.py compare it with the sources on disk. */
+const char* tg_build_id(void);
 const char* tg_last_error(void);
 int         tg_device_count(int* count);
 

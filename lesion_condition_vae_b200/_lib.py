@@ -16,7 +16,7 @@ F64, F32 = 0, 1
 
 # every symbol include/tractgeom.h declares (tests check the .so exports exactly these)
 EXPORTS = (
-    "tg_abi_version", "tg_last_error", "tg_device_count", "tg_create", "tg_destroy", "tg_synchronize",
+    "tg_abi_version", "tg_build_id", "tg_last_error", "tg_device_count", "tg_create", "tg_destroy", "tg_synchronize",
     "tg_stream", "tg_host_alloc", "tg_host_free", "tg_metrics_csr_dev", "tg_bundle_reduce_dev",
     "tg_metrics_csr_host", "tg_launch_count", "tg_bundle_spread_dev", "tg_metrics_csr_host_ex",
     "tg_resample_csr_dev", "tg_resample_csr_host",
@@ -46,6 +46,7 @@ def load():
     vp, i64, i32 = C.c_void_p, C.c_int64, C.c_int
     lib.tg_abi_version.restype = i32
     lib.tg_last_error.restype = C.c_char_p
+    lib.tg_build_id.restype = C.c_char_p
     lib.tg_device_count.argtypes = [C.POINTER(i32)]
     lib.tg_create.argtypes = [i32, C.POINTER(vp)]
     lib.tg_destroy.argtypes = [vp]
@@ -66,10 +67,15 @@ def load():
     lib.tg_metrics_csr_host_ex.argtypes = [vp, vp, i32, vp, i64, i64, vp, i64, vp, vp, vp, vp, vp]
     for name in EXPORTS:
         fn = getattr(lib, name)
-        if name not in ("tg_abi_version", "tg_last_error"):
+        if name not in ("tg_abi_version", "tg_last_error", "tg_build_id"):
             fn.restype = i32
     _lib = lib
     return lib
+
+
+def build_id():
+    """Build id compiled into the LOADED library (build.source_id() of the sources it was made from)."""
+    return load().tg_build_id().decode()
 
 
 def check(rc):

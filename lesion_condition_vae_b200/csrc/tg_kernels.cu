@@ -636,6 +636,12 @@ int plan_bundle_tiles(tg_context* c, const int64_t* h_bo, int64_t B, cudaStream_
 extern "C" {
 
 int tg_abi_version(void) { return TG_ABI_VERSION; }
+#ifndef TG_BUILD_ID
+#define TG_BUILD_ID "unidentified"
+#endif
+// "@(#)TG_BUILD_ID=" is the marker build.py looks for in the file's bytes
+static const char k_build_id[] = "@(#)TG_BUILD_ID=" TG_BUILD_ID;
+const char* tg_build_id(void) { return k_build_id + 16; }
 const char* tg_last_error(void) { return g_err; }
 
 int tg_device_count(int* count) {

@@ -138,10 +138,29 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.tg_abi_version() == 2
+    assert lib.tg_abi_version() == 3
     nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
     for name in declared:
         assert re.search(rf"\bT {name}\b", nm), name
+
+
+def test_library_is_built_from_these_sources():
+    """the binary the tests and the bench map must be the one HEAD's sources produce.  The id
+    compiled into the library (file bytes AND the loaded image) equals the sha256 id of csrc/* + tractgeom.h +
+    the nvcc command line; editing any kernel header changes the id (so a stale binary cannot go unnoticed)."""
+    from lesion_condition_vae_b200 import build as _b
+    if os.environ.get("TG_LIB"):
+        pytest.skip("tuning variant selected with TG_LIB")
+    assert _b.library_id() == _b.source_id() == _lib.build_id()
+    deps = {os.path.basename(p) for p in _b.dependency_files()}
+    assert {"tg_kernels.cu", "tg_grouped.cuh", "tg_device.cuh", "tractgeom.h"} <= deps
+    # every #include "..." of the translation unit is a tracked dependency
+    for path in _b.dependency_files():
+        for inc in re.findall(r'#include\s+"([^"]+)"', open(path).read()):
+            assert os.path.basename(inc) in deps, (path, inc)
+    # no stray library variants in the package (only the one the id check covers ships)
+    pkg = os.path.dirname(_b.LIB)
+    assert [f for f in os.listdir(pkg) if f.endswith(".so")] == ["libtractgeom.so"]
 
 
 def test_no_cpu_fallback_without_device():
