@@ -155,6 +155,91 @@ __device__ __forceinline__ void sym3_eigenvalues(double a00, double a01, double 
     l2 = fmax(lo, fmin(hi, a22));
 }
 
+// Non-iterative eigenvalues of a symmetric POSITIVE SEMI-DEFINITE 3x3 whose largest eigenvalue is isolated —
+// the covariance of an elongated point cloud, i.e. nearly every polyline (ref:119-124).  Returns false
+// (outputs untouched) when the matrix is not in that class; the caller then runs the Jacobi sweeps.
+//   1. scale by 1/trace (eigenvalues now sum to 1);
+//   2. lambda1 estimate from the trigonometric closed form in fp32 (accurate to ~1e-7: not good enough
+//      as a result, SURVEY.md F5, but a fine Newton start), then two fp64 Newton steps on
+//      det(A - x I) = 0 — the largest root is well conditioned when (l1 - l2) >= 0.05;
+//   3. deflation: v1 = the largest cross product of two rows of A - l1 I, (u, w) an orthonormal basis
+//      of its complement, and the 2x2 matrix [u w]^T A [u w] carries l2, l3 (closed form).
+// Every step has absolute error O(eps * l1), the level of LAPACK's own (measured against 50-digit
+// eigenvalues on 3000 random-walk polylines: ratios within 3.5e-12, LAPACK 2.5e-11; tests/test_highprec.py).
+__device__ __forceinline__ bool sym3_eigenvalues_fast(const double c00, const double c01, const double c02,
+                                                      const double c11, const double c12, const double c22,
+                                                      double& l1, double& l2, double& l3) {
+    const double tr = (c00 + c11) + c22;
+    if (!hi_in_range(tr, kHi_1em280, kHi_1e300)) return false;       // also rejects NaN / negative / zero
+    const double sc = rcp_fast(tr);
+    const double a00 = c00 * sc, a01 = c01 * sc, a02 = c02 * sc, a11 = c11 * sc, a12 = c12 * sc, a22 = c22 * sc;
+    // ---- fp32: closed form with the trace shifted out (q = 1/3)
+    const float third = 0.33333334f;
+    const float b00 = (float)a00 - third, b11 = (float)a11 - third, b22 = (float)a22 - third;
+    const float f01 = (float)a01, f02 = (float)a02, f12 = (float)a12;
+    const float off2 = fmaf(f01, f01, fmaf(f02, f02, f12 * f12));
+    const float p2 = fmaf(2.0f, off2, fmaf(b00, b00, fmaf(b11, b11, b22 * b22)));
+    if (!(p2 > 6e-6f)) return false;                                 // nearly isotropic: no isolated eigenvalue
+    const float ip = rsqrtf(p2 * 0.16666667f);                       // 1/p, p = sqrt(p2/6)
+    const float B00 = b00 * ip, B01 = f01 * ip, B02 = f02 * ip, B11 = b11 * ip, B12 = f12 * ip, B22 = b22 * ip;
+    const float detB = fmaf(B00, fmaf(B11, B22, -(B12 * B12)), fmaf(-B01, fmaf(B01, B22, -(B12 * B02)), B02 * fmaf(B01, B12, -(B11 * B02))));
+    const float r = fminf(fmaxf(0.5f * detB, -1.0f), 1.0f);
+    const float phi = acosf(r) * 0.33333334f;
+    const float two_p = 2.0f * __frcp_rn(ip);
+    const float e1 = fmaf(two_p, __cosf(phi), third);
+    const float e3 = fmaf(two_p, __cosf(phi + 2.0943951f), third);
+    const float e2 = (1.0f - e1) - e3;
+    if (!(e1 - e2 >= 0.05f) || !(e3 >= 2e-6f)) return false;         // l1 not isolated, or too flat for eps*l1 absolute accuracy
+    // ---- fp64: Newton on x^3 - x^2 + k1 x - k0 (trace = 1)
+    const double m0 = fma(a11, a22, -(a12 * a12)), m1 = fma(a00, a22, -(a02 * a02)), m2 = fma(a00, a11, -(a01 * a01));
+    const double k1 = (m0 + m1) + m2;
+    const double k0 = fma(a00, m0, fma(-a01, fma(a01, a22, -(a12 * a02)), a02 * fma(a01, a12, -(a11 * a02))));
+    double x = (double)e1;
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+        const double px = fma(fma(x - 1.0, x, k1), x, -k0);
+        const double dp = fma(fma(3.0, x, -2.0), x, k1);             // (x-l2)(x-l3)-ish: >= 0.05 * 0.05 near l1
+        x = fma(-px, rcp_fast(dp), x);
+    }
+    // ---- eigenvector of x: largest cross product of two rows of A - x I
+    const double d0 = a00 - x, d1 = a11 - x, d2 = a22 - x;
+    const double p0x = fma(a01, a12, -(a02 * d1)), p0y = fma(a02, a01, -(d0 * a12)), p0z = fma(d0, d1, -(a01 * a01));    // r0 x r1
+    const double p1x = fma(a01, d2, -(a02 * a12)), p1y = fma(a02, a02, -(d0 * d2)), p1z = fma(d0, a12, -(a01 * a02));    // r0 x r2
+    const double p2x = fma(d1, d2, -(a12 * a12)), p2y = fma(a12, a02, -(a01 * d2)), p2z = fma(a01, a12, -(d1 * a02));    // r1 x r2
+    const double n0 = fma(p0z, p0z, fma(p0y, p0y, p0x * p0x));
+    const double n1 = fma(p1z, p1z, fma(p1y, p1y, p1x * p1x));
+    const double n2 = fma(p2z, p2z, fma(p2y, p2y, p2x * p2x));
+    double vx = p0x, vy = p0y, vz = p0z, nn = n0;
+    if (n1 > nn) { vx = p1x; vy = p1y; vz = p1z; nn = n1; }
+    if (n2 > nn) { vx = p2x; vy = p2y; vz = p2z; nn = n2; }
+    if (!hi_in_range(nn, kHi_1em280, kHi_1e300)) return false;
+    const double rn = rsqrt_fast(nn);
+    vx *= rn; vy *= rn; vz *= rn;
+    // ---- u: v x e_i normalised, i = the smallest |v_i| (so |u| before normalisation >= sqrt(2/3)); w = v x u
+    const unsigned hx = (unsigned)__double2hiint(vx) & 0x7fffffffu, hy = (unsigned)__double2hiint(vy) & 0x7fffffffu,
+                   hz = (unsigned)__double2hiint(vz) & 0x7fffffffu;
+    double ux, uy, uz;
+    if (hx <= hy && hx <= hz) { ux = 0.0; uy = -vz; uz = vy; }
+    else if (hy <= hz) { ux = vz; uy = 0.0; uz = -vx; }
+    else { ux = -vy; uy = vx; uz = 0.0; }
+    const double ru = rsqrt_fast(fma(uz, uz, fma(uy, uy, ux * ux)));
+    ux *= ru; uy *= ru; uz *= ru;
+    const double wx = fma(vy, uz, -(vz * uy)), wy = fma(vz, ux, -(vx * uz)), wz = fma(vx, uy, -(vy * ux));
+    // ---- 2x2 block of A in the (u, w) basis
+    const double Aux = fma(a02, uz, fma(a01, uy, a00 * ux)), Auy = fma(a12, uz, fma(a11, uy, a01 * ux)), Auz = fma(a22, uz, fma(a12, uy, a02 * ux));
+    const double Awx = fma(a02, wz, fma(a01, wy, a00 * wx)), Awy = fma(a12, wz, fma(a11, wy, a01 * wx)), Awz = fma(a22, wz, fma(a12, wy, a02 * wx));
+    const double g00 = fma(uz, Auz, fma(uy, Auy, ux * Aux));
+    const double g01 = fma(uz, Awz, fma(uy, Awy, ux * Awx));
+    const double g11 = fma(wz, Awz, fma(wy, Awy, wx * Awx));
+    const double h = 0.5 * (g00 + g11), d = 0.5 * (g00 - g11);
+    const double rad2 = fma(d, d, g01 * g01);
+    const double rad = hi_in_range(rad2, kHi_1em280, kHi_1e300) ? rad2 * rsqrt_fast(rad2) : sqrt(rad2);
+    const double y2 = h + rad, y3 = h - rad;
+    if (!(y3 >= 1e-6) || !(x - y2 >= 0.04)) return false;            // l1/l3 <= 1e6: absolute error ~5 eps l1 is < 1e-9 l3
+    l1 = x * tr; l2 = y2 * tr; l3 = y3 * tr;
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------
 // Running sums of one polyline (or of one chunk of it).  Everything is additive across chunks
 // except the curvature moments, which merge with Chan's formula.

@@ -580,6 +580,13 @@ __device__ __noinline__ unsigned slow_polyline(const double* __restrict__ base, 
     return finalize_metrics(A, n, f0, f1, f2, e0, e1, e2, m0, m1, m2, out, S, s);
 }
 
+// the iterative eigen-solve as a call: rare on this path (sym3_eigenvalues_fast rejects only nearly isotropic or
+// nearly flat covariances), and ~1000 instructions that need not sit in the streaming kernel's hot code
+__device__ __noinline__ void sym3_eigenvalues_sweeps(double a00, double a01, double a02, double a11, double a12, double a22,
+                                                     double& l1, double& l2, double& l3) {
+    sym3_eigenvalues(a00, a01, a02, a11, a12, a22, l1, l2, l3);
+}
+
 // 17 metrics from the sums of a complete, well-conditioned polyline (n >= 3); column-major out.
 __device__ __forceinline__ unsigned finalize_grouped(const Sums& A, const int n,
                                                      const double f0, const double f1, const double f2,
@@ -613,7 +620,7 @@ __device__ __forceinline__ unsigned finalize_grouped(const Sums& A, const int n,
     double c00 = fma(-A.q0, g0, A.q00) * rn1, c01 = fma(-A.q0, g1, A.q01) * rn1, c02 = fma(-A.q0, g2, A.q02) * rn1;
     double c11 = fma(-A.q1, g1, A.q11) * rn1, c12 = fma(-A.q1, g2, A.q12) * rn1, c22 = fma(-A.q2, g2, A.q22) * rn1;
     double l1, l2, l3;
-    sym3_eigenvalues(c00, c01, c02, c11, c12, c22, l1, l2, l3);
+    if (!sym3_eigenvalues_fast(c00, c01, c02, c11, c12, c22, l1, l2, l3)) sym3_eigenvalues_sweeps(c00, c01, c02, c11, c12, c22, l1, l2, l3);
     st_keep(out + 10 * S + s, (l2 <= kEps) ? inf : l1 * rcp_fast(l2), pol);                        // ref:126-130
     st_keep(out + 11 * S + s, (l3 <= kEps) ? inf : l2 * rcp_fast(l3), pol);                        // ref:132-136
     st_keep(out + 12 * S + s, l1 * rcp_fast(((l1 + l2) + l3) + kEps), pol);                      // ref:138-141
