@@ -35,6 +35,24 @@ def built_library():
     print(f"[conftest] libtractgeom.so build id {_lib.build_id()}")
 
 
+def pytest_sessionfinish(session, exitstatus):
+    """Dump the parity budget (worst error / tolerance per column and case, collected by parity_rules.record) of a
+    GPU session to gpurun_out/parity_budget.json; tools/parity_budget.py turns it into profiles/parity_budget_r2.json."""
+    try:
+        import json
+        import parity_rules
+        if not parity_rules.BUDGET or not getattr(session.config.option, "markexpr", "") == "gpu":
+            return
+        from lesion_condition_vae_b200 import _lib
+        out = os.path.join(ROOT, "gpurun_out")
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_budget.json"), "w") as f:
+            json.dump({"build_id": _lib.build_id(), "exitstatus": int(exitstatus), "rule": "error / tolerance, <= 1 passes (tests/parity_rules.py)",
+                       "cases": parity_rules.BUDGET}, f, indent=1, sort_keys=True)
+    except Exception as e:                                       # never turn a reporting problem into a test failure
+        print(f"[conftest] parity budget not written: {e}")
+
+
 @pytest.fixture(autouse=True)
 def release_torch_cache(request):
     """The library allocates with cudaMalloc, outside torch's caching allocator: hand the cache back after every

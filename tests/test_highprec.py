@@ -3,8 +3,8 @@
 elongation = l1/l2, planarity = l2/l3 and anisotropy = l1/(l1+l2+l3+1e-12) come from the eigenvalues
 of a 3x3 covariance (/root/reference/src/geometry/tract_geom_proc.py:119-141).  On nearly straight
 polylines l1/l3 reaches 1e10 and LAPACK's own error in l3 is ~1e-16 l1, i.e. a RELATIVE error of
-~1e-16 l1/l3 in the ratios — the reason tests/parity_rules.py widens their tolerance to
-2e-14 l1/l3 beyond 1e-9.  Here the same ratios are recomputed from the float64 points in 60-digit
+~1e-16 l1/l3 in the ratios — the reason tests/parity_rules.py judges them by
+|d lambda| <= 1e-12 lambda1 once l1/l3 exceeds 1e5.  Here the same ratios are recomputed from the float64 points in 60-digit
 arithmetic (mpmath), so that the oracle and the CUDA path are each judged against the true value
 instead of against each other:
   * CPU: the oracle stays inside that envelope (the widening is justified, and not loose by orders
@@ -52,19 +52,24 @@ def cases():
 
 
 def judge(got, lines, strict_only=False):
-    """Max over polylines of |got - true| / tolerance for the 3 ratios; tolerance = max(1e-9, 2e-14 l1/l3) relative
+    """Max over polylines of |got - true| / tolerance for the 3 ratios, tolerance per SURVEY.md N7 (parity_rules.py):
+    1e-9 relative while l1/l3 <= 1e5; beyond, |d lambda_k| <= 1e-12 lambda1 expressed on the ratios
     (anisotropy: 1e-9 always: it does not involve the small eigenvalues)."""
+    from parity_rules import COND_STRICT, EIG_ATOL, RTOL
     worst = np.zeros(3)
     conds = []
     for row, line in zip(got, lines):
         e, p, a, cond = true_ratios(line)
         conds.append(cond)
-        if strict_only and cond > 1e5:
+        if strict_only and cond > COND_STRICT:
             continue
-        wide = max(1e-9, 2e-14 * cond)
-        for k, (g, t, tol) in enumerate(((row[10], e, wide), (row[11], p, wide), (row[12], a, 1e-9))):
+        if cond <= COND_STRICT:
+            tol_e, tol_p = RTOL * e, RTOL * p
+        else:
+            tol_e, tol_p = EIG_ATOL * e * e, EIG_ATOL * p * (cond + e)
+        for k, (g, t, tol) in enumerate(((row[10], e, tol_e), (row[11], p, tol_p), (row[12], a, RTOL * a))):
             assert np.isfinite(t) and np.isfinite(g)
-            worst[k] = max(worst[k], abs(g - t) / (tol * abs(t)))
+            worst[k] = max(worst[k], abs(g - t) / tol)
     return worst, np.asarray(conds)
 
 
@@ -73,7 +78,7 @@ def test_oracle_eigen_ratios_against_60_digit_arithmetic():
     got = np.asarray([so.metrics_row(l) for l in lines])
     worst, conds = judge(got, lines)
     assert conds.min() < 1e4 and conds.max() > 1e8            # the cases span both regimes of the rule
-    assert np.all(worst <= 1.0), f"oracle outside max(1e-9, 2e-14 l1/l3): error/tolerance = {worst}"
+    assert np.all(worst <= 1.0), f"oracle outside the N7 rule: error/tolerance = {worst}"
     strict, _ = judge(got, lines, strict_only=True)
     assert np.all(strict <= 0.05), f"oracle is >= 20x inside 1e-9 where l1/l3 <= 1e5 (error ~1e-16 l1/l3): {strict}"
 
@@ -86,6 +91,9 @@ def test_gpu_eigen_ratios_against_60_digit_arithmetic(gpu_ctx):
     assert np.all(keep == 3)
     got = table.T
     worst, _ = judge(got, lines)
-    assert np.all(worst <= 1.0), f"CUDA path outside max(1e-9, 2e-14 l1/l3): error/tolerance = {worst}"
+    assert np.all(worst <= 1.0), f"CUDA path outside the N7 rule: error/tolerance = {worst}"
     strict, _ = judge(got, lines, strict_only=True)
     assert np.all(strict <= 1.0), f"CUDA path outside 1e-9 where l1/l3 <= 1e5: {strict}"
+    from parity_rules import record
+    record("60-digit referee, l1/l3 1e2..1e10 (36 polylines)", dict(zip(("elongation_ratio", "planarity_ratio", "anisotropy_ratio"), worst)))
+    record("60-digit referee, l1/l3 <= 1e5 only", dict(zip(("elongation_ratio", "planarity_ratio", "anisotropy_ratio"), strict)))
