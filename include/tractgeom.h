@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 3   /* 2: + tg_bundle_spread_dev, tg_metrics_csr_host_ex, tg_resample_csr_*, host ingest helpers; 3: + tg_build_id (earlier entry points unchanged) */
+#define TG_ABI_VERSION 3   /* 2: + tg_bundle_spread_dev, tg_metrics_csr_host_ex, tg_resample_csr_*, host ingest helpers; 3: + tg_build_id, tg_bundle_partials_dev (earlier entry points unchanged) */
 
 #define TG_N_METRICS 17
 enum tg_metric {                 /* tract_geom_proc.py:164-187 */
@@ -108,6 +108,14 @@ int tg_metrics_csr_dev(tg_context* ctx, const void* d_xyz, int xyz_dtype, const 
 int tg_bundle_reduce_dev(tg_context* ctx, const double* d_out, const uint8_t* d_keep,
                          const uint8_t* d_select, int64_t S, const int64_t* h_bundle_offsets,
                          int64_t B, double* d_sums, int64_t* d_counts, void* stream);
+
+/* The same reduction, delivered as the multi-GPU exchange payload (the aggregate being split across
+ * GPUs is tract_geom_proc.py:191-210): d_partials float64[B x 27] = {13 sums | kept rows | 13 non-NaN counts} per bundle,
+ * counts as doubles (exact below 2^53).  A rank calls this on its CSR shard and all-gathers the B x 27 row block on the
+ * same stream; every rank then adds the gathered blocks in rank order (sharding.combine_partials). */
+int tg_bundle_partials_dev(tg_context* ctx, const double* d_out, const uint8_t* d_keep,
+                           const uint8_t* d_select, int64_t S, const int64_t* h_bundle_offsets,
+                           int64_t B, double* d_partials, void* stream);
 
 /* OPT-IN spread of the same 13 bundle columns (not part of the reference's df_bundle:
  * tract_geom_proc.py:193 defines `_safe_std` = np.nanstd and never calls it).  Call after

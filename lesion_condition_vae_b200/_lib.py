@@ -19,7 +19,7 @@ EXPORTS = (
     "tg_abi_version", "tg_build_id", "tg_last_error", "tg_device_count", "tg_create", "tg_destroy", "tg_synchronize",
     "tg_stream", "tg_host_alloc", "tg_host_free", "tg_metrics_csr_dev", "tg_bundle_reduce_dev",
     "tg_metrics_csr_host", "tg_launch_count", "tg_bundle_spread_dev", "tg_metrics_csr_host_ex",
-    "tg_resample_csr_dev", "tg_resample_csr_host",
+    "tg_resample_csr_dev", "tg_resample_csr_host", "tg_bundle_partials_dev",
     "tg_vtk_lines_to_csr", "tg_parse_ascii_f64", "tg_parse_ascii_i64",
 )
 
@@ -56,6 +56,7 @@ def load():
     lib.tg_host_free.argtypes = [vp]
     lib.tg_metrics_csr_dev.argtypes = [vp, vp, i32, vp, i64, i64, vp, vp, vp]
     lib.tg_bundle_reduce_dev.argtypes = [vp, vp, vp, vp, i64, vp, i64, vp, vp, vp]
+    lib.tg_bundle_partials_dev.argtypes = [vp, vp, vp, vp, i64, vp, i64, vp, vp]
     lib.tg_metrics_csr_host.argtypes = [vp, vp, i32, vp, i64, i64, vp, i64, vp, vp, vp, vp]
     lib.tg_launch_count.argtypes = [vp, C.POINTER(i64)]
     lib.tg_bundle_spread_dev.argtypes = [vp, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp]
@@ -134,6 +135,12 @@ class Context:
         bo = np.ascontiguousarray(bundle_offsets, dtype=np.int64)
         check(self._lib.tg_bundle_reduce_dev(self._h, d_out, d_keep, d_select or None, S, _ptr(bo), len(bo) - 1,
                                              d_sums, d_counts, stream or None))
+
+    def bundle_partials_dev(self, d_out, d_keep, d_select, S, bundle_offsets, d_partials, stream=0):
+        """Bundle partial moments as (B,27) float64 rows {13 sums | kept rows | 13 non-NaN counts}: the all-gather payload."""
+        bo = np.ascontiguousarray(bundle_offsets, dtype=np.int64)
+        check(self._lib.tg_bundle_partials_dev(self._h, d_out, d_keep, d_select or None, S, _ptr(bo), len(bo) - 1,
+                                               d_partials, stream or None))
 
     def bundle_spread_dev(self, d_out, d_keep, d_select, S, bundle_offsets, d_sums, d_counts, d_spread, stream=0):
         """Opt-in {std, min, max} of the 13 bundle columns; call after :meth:`bundle_reduce_dev` (same arguments)."""

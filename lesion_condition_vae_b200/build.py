@@ -96,6 +96,47 @@ def build(force=False, verbose=False, out=None, defines=()):
     return out
 
 
+def steady_block_stats(path=None):
+    """Static instruction mix of k_metrics_grouped's steady block (the innermost loop that processes kSub = 3 interior
+    points), read from the SASS of the built library with cuobjdump: {"fp64_pipe_per_point", "instructions_per_point",
+    "mufu_per_point"}; None when cuobjdump is missing.  bench.py reports these instead of hand-written constants."""
+    import re
+    path = path or LIB
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe) or not os.path.exists(path):
+        return None
+    try:
+        sass = subprocess.run([exe, "-sass", path], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        return None
+    ins, cur = [], None
+    for line in sass.splitlines():
+        m = re.search(r"Function : (\S+)", line)
+        if m:
+            cur = m.group(1)
+            continue
+        m = re.match(r"^\s+/\*([0-9a-f]{4,6})\*/\s+(.*?);", line)
+        if m and cur and "k_metrics_grouped" in cur:
+            ins.append((int(m.group(1), 16), m.group(2).strip()))
+    addr = {a: i for i, (a, _) in enumerate(ins)}
+    best = None
+    for i, (a, t) in enumerate(ins):
+        m = re.search(r"\bBRA(?:\.\w+)*\s+0x([0-9a-f]+)", t)
+        if not m:
+            continue
+        tgt = int(m.group(1), 16)
+        if tgt <= a and tgt in addr:
+            body = [x for _, x in ins[addr[tgt]:i + 1]]
+            ops = [re.sub(r"^@!?U?P\w+\s+", "", x).split()[0].split(".")[0] for x in body]
+            f64 = sum(o in ("DFMA", "DMUL", "DADD", "DSETP") for o in ops)
+            if f64 >= 150 and (best is None or len(body) < best[0]):      # the smallest loop that holds a whole 3-point block
+                best = (len(body), f64, sum(o == "MUFU" for o in ops))
+    if best is None:
+        return None
+    return {"fp64_pipe_per_point": best[1] / 3.0, "instructions_per_point": best[0] / 3.0, "mufu_per_point": best[2] / 3.0,
+            "source": "cuobjdump -sass of the loaded library: innermost loop of k_metrics_grouped over 3 interior points"}
+
+
 if __name__ == "__main__":
     import sys
     defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]

@@ -81,13 +81,14 @@ constexpr int kGroupedSmem = kWarpsPerCta * kWarpSmem;
 constexpr int kBins = 2048;                   // bins per queue row
 // Queue rows.  Rows 1 .. n_windows: one per window of kWindow consecutive polylines, polylines of 3 .. kShortMax
 // points, one bin per length, ascending.  Row 0 (first in the queue, so its groups start first): the polylines
-// of kShortMax+1 .. kMaxGroupedN points of the WHOLE table, 4 lengths per bin, longest first — used when there
-// are at least kLongGroupedMin of them (enough groups to keep the SMs busy); otherwise, and beyond
-// kMaxGroupedN, a polyline goes to the one-warp-per-polyline kernel.
+// of kShortMax+1 .. kMaxGroupedN points of the WHOLE table, 2 lengths per bin, longest first.  Beyond kMaxGroupedN a
+// polyline goes to the one-warp-per-polyline kernel.  The route of a polyline depends on ITS length only — never
+// on how many others there are — so its 17 numbers are bit-identical however the table is sharded across GPUs
+// or chunked by the host path (round 1 sent row 0 to the warp-per-polyline kernel when it held < 6144 polylines:
+// faster for a handful of long polylines, but the two kernels round differently).
 constexpr int kShortMax = 1024;
-constexpr int kLongShift = 2;
-constexpr int kMaxGroupedN = kShortMax + (kBins << kLongShift);
-constexpr int kLongGroupedMin = 6144;
+constexpr int kLongShift = 1;
+constexpr int kMaxGroupedN = kShortMax + (kBins << kLongShift);   // 5120
 __device__ __forceinline__ int long_bin(const int64_t n) { return kBins - 1 - (int)((n - (kShortMax + 1)) >> kLongShift); }
 #ifndef TG_WINDOW_LOG2
 #define TG_WINDOW_LOG2 17
@@ -235,7 +236,7 @@ k_window_scan(int64_t* __restrict__ wtotal, const int64_t n_windows, int64_t* __
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) {
         run = 0;
-        const bool grouped = wtotal[0] >= kLongGroupedMin;
+        const bool grouped = true;                       // by length only (see kMaxGroupedN)
         long_grouped[0] = grouped ? 1 : 0;
         if (!grouped) wtotal[0] = 0;
     }

@@ -164,9 +164,12 @@ k_bundle_tiles(const double* __restrict__ out, const uint8_t* __restrict__ keep,
 // one CTA per bundle; tile_first[b]..tile_first[b+1] are its tiles.  Thread t adds tiles t, t+256, ... in
 // order, then the 256 partials are added in a fixed tree: the result does not depend on scheduling.
 constexpr int kFinalThreads = 256;
+// `packed` != nullptr: the bundle's partial moments as ONE row of 27 doubles {13 sums | kept rows | 13 non-NaN counts}
+// (counts < 2^53 are exact) — the payload of the multi-GPU all-gather, written by this kernel so that
+// the collective can follow it on the stream with nothing in between.
 __global__ void __launch_bounds__(kFinalThreads)
 k_bundle_final(const int64_t* __restrict__ tile_first, const double* __restrict__ tsum, const int64_t* __restrict__ tcnt,
-               double* __restrict__ sums, int64_t* __restrict__ counts) {
+               double* __restrict__ sums, int64_t* __restrict__ counts, double* __restrict__ packed) {
     __shared__ double s_v[kFinalThreads];
     __shared__ long long s_c[kFinalThreads];
     const int64_t b = blockIdx.x;
@@ -185,8 +188,13 @@ k_bundle_final(const int64_t* __restrict__ tile_first, const double* __restrict_
             __syncthreads();
         }
         if (threadIdx.x == 0) {
-            if (j < kNB) sums[b * kNB + j] = s_v[0];
-            counts[b * (kNB + 1) + j] = s_c[0];
+            if (packed != nullptr) {
+                if (j < kNB) packed[b * (2 * kNB + 1) + j] = s_v[0];
+                packed[b * (2 * kNB + 1) + kNB + j] = (double)s_c[0];          // [13] = kept rows, [14 + c] = non-NaN entries of column c
+            } else {
+                if (j < kNB) sums[b * kNB + j] = s_v[0];
+                counts[b * (kNB + 1) + j] = s_c[0];
+            }
         }
         __syncthreads();
     }
@@ -812,12 +820,12 @@ int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const in
     return launch_metrics_f64(c, (const double*)d_xyz, lo, lo + 24ull * (uint64_t)P, d_offsets, S, d_out, S, d_keep, st);
 }
 
-int tg_bundle_reduce_dev(tg_context* c, const double* d_out, const uint8_t* d_keep, const uint8_t* d_select, int64_t S,
-                         const int64_t* h_bo, int64_t B, double* d_sums, int64_t* d_counts, void* stream) {
+static int bundle_reduce_impl(tg_context* c, const double* d_out, const uint8_t* d_keep, const uint8_t* d_select, int64_t S,
+                              const int64_t* h_bo, int64_t B, double* d_sums, int64_t* d_counts, double* d_packed, void* stream) {
     if (!c) return set_err(TG_E_INVALID, "null context");
     if (S < 0 || B < 0) return set_err(TG_E_INVALID, "negative size");
     if (B == 0) return TG_OK;
-    if (!h_bo || !d_sums || !d_counts || (S > 0 && (!d_out || !d_keep))) return set_err(TG_E_INVALID, "null pointer");
+    if (!h_bo || (!d_packed && (!d_sums || !d_counts)) || (S > 0 && (!d_out || !d_keep))) return set_err(TG_E_INVALID, "null pointer");
     if (h_bo[0] < 0 || h_bo[B] > S) return set_err(TG_E_INVALID, "bundle_offsets out of range");
     for (int64_t b = 0; b < B; ++b)
         if (h_bo[b + 1] < h_bo[b]) return set_err(TG_E_INVALID, "bundle_offsets must be non-decreasing");
@@ -836,10 +844,21 @@ int tg_bundle_reduce_dev(tg_context* c, const double* d_out, const uint8_t* d_ke
         tg::k_bundle_tiles<<<(unsigned)nt, tg::kBundleThreads, 0, st>>>(d_out, d_keep, d_select, S, dt, (double*)c->d_tsum.p, (int64_t*)c->d_tcnt.p);
         c->launches += 1;
     }
-    tg::k_bundle_final<<<(unsigned)B, tg::kFinalThreads, 0, st>>>(df, (const double*)c->d_tsum.p, (const int64_t*)c->d_tcnt.p, d_sums, d_counts);
+    tg::k_bundle_final<<<(unsigned)B, tg::kFinalThreads, 0, st>>>(df, (const double*)c->d_tsum.p, (const int64_t*)c->d_tcnt.p, d_sums, d_counts, d_packed);
     c->launches += 1;
     TG_CUDA(cudaGetLastError());
     return TG_OK;
+}
+
+int tg_bundle_reduce_dev(tg_context* c, const double* d_out, const uint8_t* d_keep, const uint8_t* d_select, int64_t S,
+                         const int64_t* h_bo, int64_t B, double* d_sums, int64_t* d_counts, void* stream) {
+    return bundle_reduce_impl(c, d_out, d_keep, d_select, S, h_bo, B, d_sums, d_counts, nullptr, stream);
+}
+
+int tg_bundle_partials_dev(tg_context* c, const double* d_out, const uint8_t* d_keep, const uint8_t* d_select, int64_t S,
+                           const int64_t* h_bo, int64_t B, double* d_partials, void* stream) {
+    if (!d_partials && B > 0) return set_err(TG_E_INVALID, "null pointer");
+    return bundle_reduce_impl(c, d_out, d_keep, d_select, S, h_bo, B, nullptr, nullptr, d_partials, stream);
 }
 
 int tg_bundle_spread_dev(tg_context* c, const double* d_out, const uint8_t* d_keep, const uint8_t* d_select, int64_t S,

@@ -85,3 +85,56 @@ def allgather_partials(partial, group=None):
     else:                                            # gloo has no flat all-gather: gather into views
         dist.all_gather(list(out.view(world, -1).unbind(0)), flat, group=group)
     return out.view((world,) + tuple(partial.shape))
+
+
+class DeviceShard:
+    """One rank's share of a device-resident CSR tractogram: polylines [lo, hi) of the global
+    table, cut by :func:`shard_ranges` so that every rank holds ~P/world points.
+
+    ``step()`` = tg_metrics_csr_dev on the slice, tg_bundle_partials_dev (kernel 2 writes the ``B x 27`` payload
+    itself) and ONE all-gather of that block, all enqueued back to back: no host round trip and no torch kernel
+    between kernel 2 and the collective.  ``out`` / ``keep`` hold this rank's slice of the 17 x S table; they stay
+    on the device (df_sl is gathered only when a caller wants the DataFrame)."""
+
+    def __init__(self, ctx, points, offsets, lo, hi, bundle_offsets=None, group=None, copy=False):
+        import torch
+        self.ctx, self.group = ctx, group
+        self.lo, self.hi = int(lo), int(hi)
+        p0, p1 = int(offsets[self.lo]), int(offsets[self.hi])
+        self.S = self.hi - self.lo
+        # The slice carries PAD readable points behind its last polyline (the next shard's first points, or zeros):
+        # the staging of the streaming kernel reads whole 16-byte pieces and sends a polyline that ends flush with the
+        # end of the array to its exact (differently rounded) path — with the slack no shard boundary does that, so a
+        # polyline's row is bit-identical to the single-GPU one.  P counts the padded array; offsets never reach it.
+        PAD = 2
+        tail = points[p1:p1 + PAD]
+        if copy or tail.shape[0] < PAD:
+            buf = torch.zeros((p1 - p0 + PAD, 3), dtype=points.dtype, device=points.device)
+            buf[:p1 - p0 + tail.shape[0]] = points[p0:p1 + tail.shape[0]]
+            self.points = buf                                               # an own copy: the global table can be freed
+        else:
+            self.points = points[p0:p1 + PAD]                               # a view of the global table
+        self.offsets = (offsets[self.lo:self.hi + 1] - p0).contiguous()
+        self.P = p1 - p0 + PAD
+        dev = points.device
+        S_all = int(offsets.numel()) - 1
+        bo = np.array([0, S_all], dtype=np.int64) if bundle_offsets is None else np.asarray(bundle_offsets, dtype=np.int64)
+        self.bundle_offsets = shard_bundle_offsets(bo, self.lo, self.hi)
+        self.B = len(bo) - 1
+        self.out = torch.empty((17, max(self.S, 1)), dtype=torch.float64, device=dev)
+        self.keep = torch.empty(max(self.S, 1), dtype=torch.uint8, device=dev)
+        self.partial = torch.zeros((self.B, PARTIAL_WIDTH), dtype=torch.float64, device=dev)
+
+    def compute(self, stream=0):
+        """Kernels only (metrics + packed bundle partials) on ``stream``."""
+        from . import _lib
+        if self.S > 0:
+            self.ctx.metrics_dev(self.points.data_ptr(), _lib.F64, self.offsets.data_ptr(), self.S, self.P,
+                                 self.out.data_ptr(), self.keep.data_ptr(), stream)
+        self.ctx.bundle_partials_dev(self.out.data_ptr(), self.keep.data_ptr(), 0, self.S, self.bundle_offsets,
+                                     self.partial.data_ptr(), stream)
+
+    def step(self, stream=0):
+        """compute() + the all-gather; returns the (world, B, 27) tensor every rank then sums in rank order."""
+        self.compute(stream)
+        return allgather_partials(self.partial, self.group)

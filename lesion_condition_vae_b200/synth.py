@@ -171,8 +171,10 @@ def torch_lengths(kind, S, seed, device):
     if kind == "loguniform":
         u = torch.rand(S, generator=g, device=device, dtype=torch.float64)
         return torch.clamp(torch.floor(10.0 * torch.pow(torch.tensor(500.0, dtype=torch.float64, device=device), u)), max=5000.0).to(torch.int64)
-    if kind == "uniform":
+    if kind == "uniform":                      # BASELINE configs[0]: n ~ U{20..119}
         return torch.randint(20, 120, (S,), generator=g, device=device, dtype=torch.int64)
+    if kind == "uniform40":                    # BASELINE configs[1]: n ~ U{40..139}
+        return torch.randint(40, 140, (S,), generator=g, device=device, dtype=torch.int64)
     if kind == "fixed96":                      # every polyline 96 points = 36 whole 64-byte atoms (traffic probe)
         return torch.full((S,), 96, device=device, dtype=torch.int64)
     raise ValueError(kind)
