@@ -102,20 +102,22 @@ class DeviceShard:
         self.lo, self.hi = int(lo), int(hi)
         p0, p1 = int(offsets[self.lo]), int(offsets[self.hi])
         self.S = self.hi - self.lo
-        # The slice carries PAD readable points behind its last polyline (the next shard's first points, or zeros):
-        # the staging of the streaming kernel reads whole 16-byte pieces and sends a polyline that ends flush with the
-        # end of the array to its exact (differently rounded) path — with the slack no shard boundary does that, so a
-        # polyline's row is bit-identical to the single-GPU one.  P counts the padded array; offsets never reach it.
-        PAD = 2
-        tail = points[p1:p1 + PAD]
-        if copy or tail.shape[0] < PAD:
-            buf = torch.zeros((p1 - p0 + PAD, 3), dtype=points.dtype, device=points.device)
-            buf[:p1 - p0 + tail.shape[0]] = points[p0:p1 + tail.shape[0]]
-            self.points = buf                                               # an own copy: the global table can be freed
+        # The slice carries readable slack on both sides — LEAD points in front (the previous shard's last points) and
+        # PAD behind (the next shard's first points), zeros where the table ends.  The streaming kernel stages whole
+        # 32-byte sectors / 16-byte pieces and sends a polyline whose staging would leave the array to its exact,
+        # differently rounded, path; with the slack no shard boundary does that, so every polyline's row is
+        # bit-identical to the single-GPU one.  P counts the padded array; offsets are rebased by LEAD.
+        LEAD, PAD = (4 if p0 > 0 else 0), 2                # 4 points = 96 bytes: keeps 32-byte alignment classes
+        total = int(points.shape[0])
+        if not copy and p0 >= LEAD and p1 + PAD <= total:
+            self.points = points[p0 - LEAD:p1 + PAD]                        # a view of the global table
         else:
-            self.points = points[p0:p1 + PAD]                               # a view of the global table
-        self.offsets = (offsets[self.lo:self.hi + 1] - p0).contiguous()
-        self.P = p1 - p0 + PAD
+            a, b = max(p0 - LEAD, 0), min(p1 + PAD, total)
+            buf = torch.zeros((LEAD + (p1 - p0) + PAD, 3), dtype=points.dtype, device=points.device)
+            buf[LEAD - (p0 - a):LEAD + (b - p0)] = points[a:b]
+            self.points = buf                                               # an own copy: the global table can be freed
+        self.offsets = (offsets[self.lo:self.hi + 1] - (p0 - LEAD)).contiguous()
+        self.P = LEAD + (p1 - p0) + PAD
         dev = points.device
         S_all = int(offsets.numel()) - 1
         bo = np.array([0, S_all], dtype=np.int64) if bundle_offsets is None else np.asarray(bundle_offsets, dtype=np.int64)
