@@ -35,7 +35,8 @@
 extern "C" {
 #endif
 
-#define TG_ABI_VERSION 3   /* 2: + tg_bundle_spread_dev, tg_metrics_csr_host_ex, tg_resample_csr_*, host ingest helpers; 3: + tg_build_id, tg_bundle_partials_dev (earlier entry points unchanged) */
+#define TG_ABI_VERSION 3   /* 2: + tg_bundle_spread_dev, tg_metrics_csr_host_ex, tg_resample_csr_*, host ingest helpers; 3: + tg_build_id,
+                              tg_bundle_partials_dev, tg_batch_*, big-endian point storage (earlier entry points unchanged) */
 
 #define TG_N_METRICS 17
 enum tg_metric {                 /* tract_geom_proc.py:164-187 */
@@ -65,7 +66,9 @@ enum tg_status {
     TG_E_NODEVICE = -4    /* no usable CUDA device: there is NO CPU fallback */
 };
 
-enum tg_dtype { TG_F64 = 0, TG_F32 = 1 };
+/* Point storage.  The _BE forms are what a legacy BINARY VTK file holds (`POINTS n float|double`, big-endian): the loader
+ * hands the file's bytes over as they are and the byte swap / exact upcast to float64 happens on the device. */
+enum tg_dtype { TG_F64 = 0, TG_F32 = 1, TG_F64_BE = 2, TG_F32_BE = 3 };
 
 typedef struct tg_context tg_context;
 
@@ -141,6 +144,18 @@ int tg_metrics_csr_host_ex(tg_context* ctx, const void* h_xyz, int xyz_dtype, co
                            int64_t S, int64_t P, const int64_t* h_bundle_offsets, int64_t B,
                            double* h_out, uint8_t* h_keep, double* h_sums, int64_t* h_counts,
                            double* h_spread);
+
+/* A BATCH of tract files in one device call (the loop at comprehensive_tract_geometry_analysis.py:169-195 makes 2,368
+ * separate calls): begin with capacities, PUSH every file's points as soon as it is parsed — the host-to-device copy
+ * is queued on a copy stream and returns at once when h_xyz is pinned (tg_host_alloc), so parsing file i+1 overlaps
+ * the transfer of file i; the buffer must stay untouched until tg_batch_run returns — then RUN: metrics of all pushed
+ * polylines + the bundle reduction over h_bundle_offsets (indices into the concatenated polylines, usually one bundle
+ * per file).  Files may differ in storage type.  h_out (17 x S_total, column-major), h_keep, h_spread may be NULL. */
+int tg_batch_begin(tg_context* ctx, int64_t P_capacity, int64_t S_capacity);
+int tg_batch_push(tg_context* ctx, const void* h_xyz, int xyz_dtype, int64_t P, const int64_t* h_offsets, int64_t S);
+int tg_batch_run(tg_context* ctx, const int64_t* h_bundle_offsets, int64_t B, double* h_out, uint8_t* h_keep,
+                 double* h_sums, int64_t* h_counts, double* h_spread);
+int tg_batch_size(tg_context* ctx, int64_t* S_total, int64_t* P_total);
 
 /* Arc-length resampling of every polyline to n_nodes points: the ragged-to-fixed step in
  * front of src/vae/data_loader.py:94-100, which expects exactly 100 `point_id`s per streamline and for which

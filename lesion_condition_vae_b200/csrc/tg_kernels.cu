@@ -82,17 +82,36 @@ k_metrics_long(const double* __restrict__ xyz, const int64_t* __restrict__ offse
     }
 }
 
-// float32 storage: exact upcast into a float64 scratch copy, then the float64 path (so a float32
-// file gives bit-identical results to the same values stored as float64)
+// Point storage other than native float64 -> a float64 scratch copy, then the float64 path: float32 is upcast exactly
+// (a float32 file gives bit-identical results to the same values stored as float64), and the BIG-ENDIAN
+// forms are what a legacy binary VTK file holds (`POINTS n float|double`): the loader ships the file's bytes as they
+// are — into pinned memory, no per-point work on the host — and the byte swap happens here, at HBM speed.
+__device__ __forceinline__ double decode_f32(uint32_t w, const bool swap) {
+    if (swap) w = __byte_perm(w, 0u, 0x0123);
+    return (double)__uint_as_float(w);
+}
+__device__ __forceinline__ double decode_f64(const uint2 w, const bool swap) {
+    // little-endian memory order: w.x = bytes 0..3, w.y = bytes 4..7; big-endian value = reverse all 8 bytes
+    const uint32_t lo = swap ? __byte_perm(w.y, 0u, 0x0123) : w.x;
+    const uint32_t hi = swap ? __byte_perm(w.x, 0u, 0x0123) : w.y;
+    return __hiloint2double((int)hi, (int)lo);
+}
+template <bool F32>
 __global__ void __launch_bounds__(256)
-k_upcast_f32(const float* __restrict__ src, double* __restrict__ dst, const int64_t count) {
+k_decode_points(const void* __restrict__ src, double* __restrict__ dst, const int64_t count, const int swap) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
     for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < count; i += stride) {
-        if (i + 3 < count && (((uintptr_t)(src + i)) & 15u) == 0) {
-            const float4 v = *reinterpret_cast<const float4*>(src + i);
-            dst[i] = (double)v.x; dst[i + 1] = (double)v.y; dst[i + 2] = (double)v.z; dst[i + 3] = (double)v.w;
+        if (F32) {
+            const uint32_t* s = (const uint32_t*)src + i;
+            if (i + 3 < count && (((uintptr_t)s) & 15u) == 0) {
+                const uint4 v = *reinterpret_cast<const uint4*>(s);
+                dst[i] = decode_f32(v.x, swap); dst[i + 1] = decode_f32(v.y, swap); dst[i + 2] = decode_f32(v.z, swap); dst[i + 3] = decode_f32(v.w, swap);
+            } else {
+                for (int64_t j = i; j < count && j < i + 4; ++j) dst[j] = decode_f32(((const uint32_t*)src)[j], swap);
+            }
         } else {
-            for (int64_t j = i; j < count && j < i + 4; ++j) dst[j] = (double)src[j];
+            const uint2* s = (const uint2*)src + i;      // 8-byte aligned by contract
+            for (int64_t j = 0; j < 4 && i + j < count; ++j) dst[i + j] = decode_f64(s[j], swap);
         }
     }
 }
@@ -571,6 +590,12 @@ struct tg_context {
     DevBuf d_tiles, d_tsum, d_tcnt, d_tspread;
     // host-path scratch
     DevBuf d_xyz, d_off, d_out, d_keep, d_sums, d_counts, d_spread, d_nodes;
+    // batch (tg_batch_*): raw bytes as pushed, their float64 decode, offsets assembled on the host
+    DevBuf d_braw, d_bxyz;
+    PinBuf h_boff;
+    cudaEvent_t ev_push = nullptr;
+    int64_t b_P = 0, b_S = 0, b_Pcap = -1, b_Scap = -1;
+    size_t b_raw = 0;
 };
 
 namespace {
@@ -584,15 +609,6 @@ struct DeviceGuard {
     }
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
-
-// a kernel may raise a word in device memory (+32 in the queue header) to report a failed invariant
-int check_pipeline_error(tg_context* c) {
-    if (!c->d_qhead.p) return TG_OK;
-    int e = 0;
-    TG_CUDA(cudaMemcpy(&e, (char*)c->d_qhead.p + 32, sizeof(int), cudaMemcpyDeviceToHost));
-    if (e != 0) return set_err(TG_E_CUDA, "device pipeline error %s; results are invalid", std::to_string(e).c_str());
-    return TG_OK;
-}
 
 int upload_bundle_src() {
     static thread_local int done_for = -1;
@@ -701,6 +717,8 @@ int tg_destroy(tg_context* c) {
     c->d_xyz.release(); c->d_off.release(); c->d_out.release(); c->d_keep.release();
     c->d_sums.release(); c->d_counts.release(); c->d_spread.release(); c->d_tspread.release(); c->d_nodes.release();
     c->d_xyz64.release(); c->d_qhead.release(); c->d_hist.release(); c->d_start.release(); c->d_perm.release();
+    c->d_braw.release(); c->d_bxyz.release(); c->h_boff.release();
+    if (c->ev_push) cudaEventDestroy(c->ev_push);
     if (c->s_copy) { cudaStreamDestroy(c->s_copy); cudaStreamDestroy(c->s_back); for (int i = 0; i < 2; ++i) { cudaEventDestroy(c->ev_h2d[i]); cudaEventDestroy(c->ev_comp[i]); } }
     cudaEventDestroy(c->staged);
     cudaStreamDestroy(c->stream);
@@ -712,7 +730,7 @@ int tg_synchronize(tg_context* c) {
     if (!c) return set_err(TG_E_INVALID, "null context");
     DeviceGuard g(c->device);
     TG_CUDA(cudaStreamSynchronize(c->stream));
-    return check_pipeline_error(c);
+    return TG_OK;
 }
 
 int tg_stream(tg_context* c, void** stream) {
@@ -770,7 +788,7 @@ static int launch_metrics_f64(tg_context* c, const double* xyz, uint64_t lo, uin
     int64_t* d_start = (int64_t*)c->d_start.p;
     int64_t* d_wbase = d_start + tg::kBins * n_windows;          // per-window totals, then bases
     uint4* d_queue = (uint4*)c->d_perm.p;
-    TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 32, st));          // n_long, total, ticket, long_grouped (the pipeline error word at +32 is sticky)
+    TG_CUDA(cudaMemsetAsync(c->d_qhead.p, 0, 32, st));          // n_long, total, ticket, long_grouped
     TG_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(unsigned) * tg::kBins * (size_t)n_windows, st));
     const unsigned seg_grid = (unsigned)((S + tg::kBinSeg - 1) / tg::kBinSeg);
     tg::k_bin_count<<<seg_grid, tg::kBinThreads, 0, st>>>(d_offsets, S, d_hist);
@@ -789,12 +807,18 @@ static int launch_metrics_f64(tg_context* c, const double* xyz, uint64_t lo, uin
     return TG_OK;
 }
 
-static int upcast_f32(tg_context* c, const void* d_src, int64_t count, double* d_dst, cudaStream_t st) {
+static inline bool dtype_ok(int t) { return t == TG_F64 || t == TG_F32 || t == TG_F64_BE || t == TG_F32_BE; }
+static inline size_t dtype_size(int t) { return (t == TG_F64 || t == TG_F64_BE) ? 8 : 4; }
+
+// any storage form -> native float64 (count = number of coordinates)
+static int decode_points(tg_context* c, const void* d_src, int xyz_dtype, int64_t count, double* d_dst, cudaStream_t st) {
     if (count <= 0) return TG_OK;
     const int64_t want = (count / 4 + 255) / 256;
     const int64_t cap = (int64_t)c->sm_count * 16;
     const unsigned g = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
-    tg::k_upcast_f32<<<g, 256, 0, st>>>((const float*)d_src, d_dst, count);
+    const int swap = (xyz_dtype == TG_F64_BE || xyz_dtype == TG_F32_BE) ? 1 : 0;
+    if (dtype_size(xyz_dtype) == 4) tg::k_decode_points<true><<<g, 256, 0, st>>>(d_src, d_dst, count, swap);
+    else tg::k_decode_points<false><<<g, 256, 0, st>>>(d_src, d_dst, count, swap);
     c->launches += 1;
     TG_CUDA(cudaGetLastError());
     return TG_OK;
@@ -804,15 +828,15 @@ int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const in
                        double* d_out, uint8_t* d_keep, void* stream) {
     if (!c) return set_err(TG_E_INVALID, "null context");
     if (S < 0 || P < 0) return set_err(TG_E_INVALID, "negative size");
-    if (xyz_dtype != TG_F64 && xyz_dtype != TG_F32) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64 or TG_F32");
+    if (!dtype_ok(xyz_dtype)) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64, TG_F32, TG_F64_BE or TG_F32_BE");
     if (S == 0) return TG_OK;
     if (!d_offsets || !d_out || !d_keep || (P > 0 && !d_xyz)) return set_err(TG_E_INVALID, "null device pointer");
     DeviceGuard g(c->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     int rc;
-    if (xyz_dtype == TG_F32) {
+    if (xyz_dtype != TG_F64) {
         if ((rc = c->d_xyz64.reserve(sizeof(double) * 3 * (size_t)P + 64))) return rc;
-        if ((rc = upcast_f32(c, d_xyz, 3 * P, (double*)c->d_xyz64.p, st))) return rc;
+        if ((rc = decode_points(c, d_xyz, xyz_dtype, 3 * P, (double*)c->d_xyz64.p, st))) return rc;
         d_xyz = c->d_xyz64.p;
     }
     if (((uintptr_t)d_xyz & 7u) != 0) return set_err(TG_E_INVALID, "xyz must be 8-byte aligned");
@@ -894,15 +918,15 @@ int tg_resample_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const i
     if (!c) return set_err(TG_E_INVALID, "null context");
     if (S < 0 || P < 0) return set_err(TG_E_INVALID, "negative size");
     if (n_nodes < 2) return set_err(TG_E_INVALID, "n_nodes must be at least 2");
-    if (xyz_dtype != TG_F64 && xyz_dtype != TG_F32) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64 or TG_F32");
+    if (!dtype_ok(xyz_dtype)) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64, TG_F32, TG_F64_BE or TG_F32_BE");
     if (S == 0) return TG_OK;
     if (!d_offsets || !d_nodes || (P > 0 && !d_xyz)) return set_err(TG_E_INVALID, "null device pointer");
     DeviceGuard g(c->device);
     cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
     int rc;
-    if (xyz_dtype == TG_F32) {
+    if (xyz_dtype != TG_F64) {
         if ((rc = c->d_xyz64.reserve(sizeof(double) * 3 * (size_t)P + 64))) return rc;
-        if ((rc = upcast_f32(c, d_xyz, 3 * P, (double*)c->d_xyz64.p, st))) return rc;
+        if ((rc = decode_points(c, d_xyz, xyz_dtype, 3 * P, (double*)c->d_xyz64.p, st))) return rc;
         d_xyz = c->d_xyz64.p;
     }
     if (((uintptr_t)d_xyz & 7u) != 0) return set_err(TG_E_INVALID, "xyz must be 8-byte aligned");
@@ -925,14 +949,14 @@ int tg_resample_csr_host(tg_context* c, const void* h_xyz, int xyz_dtype, const 
     if (!c) return set_err(TG_E_INVALID, "null context");
     if (S < 0 || P < 0) return set_err(TG_E_INVALID, "negative size");
     if (n_nodes < 2) return set_err(TG_E_INVALID, "n_nodes must be at least 2");
-    if (xyz_dtype != TG_F64 && xyz_dtype != TG_F32) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64 or TG_F32");
+    if (!dtype_ok(xyz_dtype)) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64, TG_F32, TG_F64_BE or TG_F32_BE");
     if (S == 0) return TG_OK;
     if (!h_off || !h_nodes || (P > 0 && !h_xyz)) return set_err(TG_E_INVALID, "null pointer");
     if (h_off[0] < 0 || h_off[S] > P) return set_err(TG_E_INVALID, "offsets out of range of the point array");
     for (int64_t s = 0; s < S; ++s)
         if (h_off[s + 1] < h_off[s]) return set_err(TG_E_INVALID, "offsets must be non-decreasing");
     DeviceGuard g(c->device);
-    const size_t esz = xyz_dtype == TG_F64 ? 8 : 4;
+    const size_t esz = dtype_size(xyz_dtype);
     const size_t node_bytes = sizeof(double) * 3 * (size_t)n_nodes * (size_t)S;
     int rc;
     if ((rc = c->d_xyz.reserve(esz * 3 * (size_t)P + 64))) return rc;
@@ -1012,12 +1036,34 @@ int tg_metrics_csr_host(tg_context* c, const void* h_xyz, int xyz_dtype, const i
     return tg_metrics_csr_host_ex(c, h_xyz, xyz_dtype, h_off, S, P, h_bo, B, h_out, h_keep, h_sums, h_counts, nullptr);
 }
 
+static int host_pipeline(tg_context* c, const void* h_xyz, int xyz_dtype, const int64_t* h_off, int64_t S, int64_t P,
+                         const int64_t* h_bo, int64_t B, double* h_out, uint8_t* h_keep, double* h_sums, int64_t* h_counts,
+                         double* h_spread);
+static int ensure_side_streams(tg_context* c);
+
+// copies issued by a failed call may still be reading / writing the caller's buffers: drain before returning the error
+static void drain_streams(tg_context* c) {
+    if (c->s_copy) cudaStreamSynchronize(c->s_copy);
+    cudaStreamSynchronize(c->stream);
+    if (c->s_back) cudaStreamSynchronize(c->s_back);
+    cudaGetLastError();
+}
+
 int tg_metrics_csr_host_ex(tg_context* c, const void* h_xyz, int xyz_dtype, const int64_t* h_off, int64_t S, int64_t P,
                            const int64_t* h_bo, int64_t B, double* h_out, uint8_t* h_keep, double* h_sums, int64_t* h_counts,
                            double* h_spread) {
     if (!c) return set_err(TG_E_INVALID, "null context");
+    const int rc = host_pipeline(c, h_xyz, xyz_dtype, h_off, S, P, h_bo, B, h_out, h_keep, h_sums, h_counts, h_spread);
+    if (rc != TG_OK) drain_streams(c);
+    return rc;
+}
+
+static int host_pipeline(tg_context* c, const void* h_xyz, int xyz_dtype, const int64_t* h_off, int64_t S, int64_t P,
+                         const int64_t* h_bo, int64_t B, double* h_out, uint8_t* h_keep, double* h_sums, int64_t* h_counts,
+                         double* h_spread) {
+    if (!c) return set_err(TG_E_INVALID, "null context");
     if (S < 0 || P < 0 || B < 0) return set_err(TG_E_INVALID, "negative size");
-    if (xyz_dtype != TG_F64 && xyz_dtype != TG_F32) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64 or TG_F32");
+    if (!dtype_ok(xyz_dtype)) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64, TG_F32, TG_F64_BE or TG_F32_BE");
     if (!h_off) return set_err(TG_E_INVALID, "null offsets");
     if (P > 0 && !h_xyz) return set_err(TG_E_INVALID, "null xyz");
     if (B > 0 && (!h_bo || !h_sums || !h_counts)) return set_err(TG_E_INVALID, "null bundle argument");
@@ -1028,7 +1074,7 @@ int tg_metrics_csr_host_ex(tg_context* c, const void* h_xyz, int xyz_dtype, cons
         if (n > 0x7ffffff0LL) return set_err(TG_E_INVALID, "a polyline has more than 2^31-16 points");
     }
     DeviceGuard g(c->device);
-    const size_t esz = xyz_dtype == TG_F64 ? 8 : 4;
+    const size_t esz = dtype_size(xyz_dtype);
     int rc;
     // ---- chunk plan: contiguous polyline ranges of at most ~chunk_points points each, so that the
     //      H2D copy of chunk i+1, the kernels of chunk i and the D2H of chunk i-1 overlap
@@ -1051,21 +1097,14 @@ int tg_metrics_csr_host_ex(tg_context* c, const void* h_xyz, int xyz_dtype, cons
     // just because of where the chunk boundary fell (results do not depend on the chunking)
     const size_t buf_stride = ((esz * 3 * (size_t)max_pts + 255) & ~(size_t)255) + 512;
     if ((rc = c->d_xyz.reserve(2 * buf_stride))) return rc;
-    if (xyz_dtype == TG_F32 && (rc = c->d_xyz64.reserve(sizeof(double) * 3 * (size_t)max_pts + 512))) return rc;
+    if (xyz_dtype != TG_F64 && (rc = c->d_xyz64.reserve(sizeof(double) * 3 * (size_t)max_pts + 512))) return rc;
     if ((rc = c->d_off.reserve(sizeof(int64_t) * (size_t)(S + 1)))) return rc;
     if ((rc = c->d_out.reserve(sizeof(double) * TG_N_METRICS * (size_t)S))) return rc;
     if ((rc = c->d_keep.reserve((size_t)S))) return rc;
     if ((rc = c->d_sums.reserve(sizeof(double) * tg::kNB * (size_t)B))) return rc;
     if ((rc = c->d_counts.reserve(sizeof(int64_t) * (tg::kNB + 1) * (size_t)B))) return rc;
     if (h_spread && (rc = c->d_spread.reserve(sizeof(double) * 3 * tg::kNB * (size_t)B))) return rc;
-    if (!c->s_copy) {
-        TG_CUDA(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
-        TG_CUDA(cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            TG_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
-            TG_CUDA(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
-        }
-    }
+    if ((rc = ensure_side_streams(c))) return rc;
     cudaStream_t st = c->stream;
     double* d_out = (double*)c->d_out.p;
     uint8_t* d_keep = (uint8_t*)c->d_keep.p;
@@ -1080,8 +1119,8 @@ int tg_metrics_csr_host_ex(tg_context* c, const void* h_xyz, int xyz_dtype, cons
         TG_CUDA(cudaEventRecord(c->ev_h2d[b], c->s_copy));
         TG_CUDA(cudaStreamWaitEvent(st, c->ev_h2d[b], 0));
         const double* d_pts = (const double*)d_buf;
-        if (xyz_dtype == TG_F32) {
-            if ((rc = upcast_f32(c, d_buf, 3 * np, (double*)((char*)c->d_xyz64.p + 256), st))) return rc;
+        if (xyz_dtype != TG_F64) {
+            if ((rc = decode_points(c, d_buf, xyz_dtype, 3 * np, (double*)((char*)c->d_xyz64.p + 256), st))) return rc;
             d_pts = (const double*)((char*)c->d_xyz64.p + 256);
         }
         const uint64_t lo = (uint64_t)(uintptr_t)d_pts;
@@ -1090,9 +1129,9 @@ int tg_metrics_csr_host_ex(tg_context* c, const void* h_xyz, int xyz_dtype, cons
         TG_CUDA(cudaEventRecord(c->ev_comp[b], st));
         if (h_out || h_keep) {
             TG_CUDA(cudaStreamWaitEvent(c->s_back, c->ev_comp[b], 0));
-            if (h_out)
-                for (int m = 0; m < TG_N_METRICS; ++m)
-                    TG_CUDA(cudaMemcpyAsync(h_out + (size_t)m * S + s0, d_out + (size_t)m * S + s0, sizeof(double) * (size_t)(s1 - s0), cudaMemcpyDeviceToHost, c->s_back));
+            if (h_out)      // the chunk's 17 column slices in ONE strided copy (pitch = a whole column)
+                TG_CUDA(cudaMemcpy2DAsync(h_out + s0, sizeof(double) * (size_t)S, d_out + s0, sizeof(double) * (size_t)S,
+                                          sizeof(double) * (size_t)(s1 - s0), TG_N_METRICS, cudaMemcpyDeviceToHost, c->s_back));
             if (h_keep) TG_CUDA(cudaMemcpyAsync(h_keep + s0, d_keep + s0, (size_t)(s1 - s0), cudaMemcpyDeviceToHost, c->s_back));
         }
     }
@@ -1109,7 +1148,166 @@ int tg_metrics_csr_host_ex(tg_context* c, const void* h_xyz, int xyz_dtype, cons
     TG_CUDA(cudaStreamSynchronize(c->s_copy));
     TG_CUDA(cudaStreamSynchronize(st));
     TG_CUDA(cudaStreamSynchronize(c->s_back));
-    return check_pipeline_error(c);
+    return TG_OK;
+}
+
+// ---- batch of files: points pushed file by file, one device call at the end ----------------
+static int ensure_side_streams(tg_context* c) {
+    if (!c->s_copy) {
+        TG_CUDA(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+        TG_CUDA(cudaStreamCreateWithFlags(&c->s_back, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            TG_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+            TG_CUDA(cudaEventCreateWithFlags(&c->ev_comp[i], cudaEventDisableTiming));
+        }
+    }
+    if (!c->ev_push) TG_CUDA(cudaEventCreateWithFlags(&c->ev_push, cudaEventDisableTiming));
+    return TG_OK;
+}
+
+// more room for a running batch: new device buffers, the pushed part copied over behind the pending transfers
+static int batch_grow(tg_context* c, int64_t need_P, int64_t need_S) {
+    if (need_S > c->b_Scap) {
+        const int64_t cap = std::max<int64_t>(need_S, 2 * c->b_Scap);
+        PinBuf nb;
+        int rc = nb.reserve(sizeof(int64_t) * (size_t)(cap + 1));
+        if (rc) return rc;
+        memcpy(nb.p, c->h_boff.p, sizeof(int64_t) * (size_t)(c->b_S + 1));
+        c->h_boff.release();
+        c->h_boff = nb;
+        c->b_Scap = cap;
+    }
+    if (need_P > c->b_Pcap) {
+        const int64_t cap = std::max<int64_t>(need_P, 2 * c->b_Pcap);
+        DevBuf nxyz;
+        int rc;
+        if ((rc = nxyz.reserve(24 * (size_t)cap + 1024))) return rc;
+        TG_CUDA(cudaStreamSynchronize(c->s_copy));                   // pushed copies have landed; decodes are ordered on the main stream
+        if (c->b_P > 0)
+            TG_CUDA(cudaMemcpyAsync((char*)nxyz.p + 256, (char*)c->d_bxyz.p + 256, 24 * (size_t)c->b_P, cudaMemcpyDeviceToDevice, c->stream));
+        TG_CUDA(cudaStreamSynchronize(c->stream));
+        c->d_bxyz.release();
+        c->d_bxyz = nxyz;
+        c->b_Pcap = cap;
+    }
+    return TG_OK;
+}
+
+int tg_batch_begin(tg_context* c, int64_t P_cap, int64_t S_cap) {
+    if (!c) return set_err(TG_E_INVALID, "null context");
+    if (P_cap < 0 || S_cap < 0) return set_err(TG_E_INVALID, "negative size");
+    DeviceGuard g(c->device);
+    int rc;
+    if ((rc = ensure_side_streams(c))) return rc;
+    TG_CUDA(cudaStreamSynchronize(c->stream));                       // a previous batch may still read the buffers
+    if ((rc = c->d_braw.reserve(std::min<size_t>(24 * (size_t)P_cap + 512, (size_t)64 << 20)))) return rc;
+    if ((rc = c->d_bxyz.reserve(24 * (size_t)P_cap + 1024))) return rc;
+    if ((rc = c->h_boff.reserve(sizeof(int64_t) * (size_t)(S_cap + 1)))) return rc;
+    c->b_P = 0; c->b_S = 0; c->b_raw = 0; c->b_Pcap = P_cap; c->b_Scap = S_cap;
+    ((int64_t*)c->h_boff.p)[0] = 0;
+    return TG_OK;
+}
+
+int tg_batch_push(tg_context* c, const void* h_xyz, int xyz_dtype, int64_t P_i, const int64_t* h_off, int64_t S_i) {
+    if (!c) return set_err(TG_E_INVALID, "null context");
+    if (c->b_Pcap < 0) return set_err(TG_E_INVALID, "tg_batch_push without tg_batch_begin");
+    if (!dtype_ok(xyz_dtype)) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64, TG_F32, TG_F64_BE or TG_F32_BE");
+    if (P_i < 0 || S_i < 0 || (S_i > 0 && !h_off) || (P_i > 0 && !h_xyz)) return set_err(TG_E_INVALID, "bad argument");
+    if (S_i > 0 && h_off[S_i] >= 0 && h_off[S_i] < P_i) P_i = h_off[S_i];   // points behind the last polyline are not part of the table
+    if (S_i == 0) P_i = 0;
+    if (c->b_P + P_i > c->b_Pcap || c->b_S + S_i > c->b_Scap) {        // capacities are hints: grow by doubling, keeping what was pushed
+        DeviceGuard g2(c->device);
+        int rc = batch_grow(c, c->b_P + P_i, c->b_S + S_i);
+        if (rc) return rc;
+    }
+    if (S_i > 0 && (h_off[0] != 0 || h_off[S_i] > P_i)) return set_err(TG_E_INVALID, "offsets must start at 0 and stay inside the point array");
+    int64_t* bo = (int64_t*)c->h_boff.p;
+    for (int64_t s = 0; s < S_i; ++s) {
+        const int64_t n = h_off[s + 1] - h_off[s];
+        if (n < 0) return set_err(TG_E_INVALID, "offsets must be non-decreasing");
+        if (n > 0x7ffffff0LL) return set_err(TG_E_INVALID, "a polyline has more than 2^31-16 points");
+        bo[c->b_S + s + 1] = c->b_P + h_off[s + 1];
+    }
+    DeviceGuard g(c->device);
+    if (P_i > 0) {
+        const size_t esz = dtype_size(xyz_dtype), bytes = esz * 3 * (size_t)P_i;
+        double* dst = (double*)((char*)c->d_bxyz.p + 256) + 3 * c->b_P;
+        if (xyz_dtype == TG_F64) {                                   // native: straight into place
+            TG_CUDA(cudaMemcpyAsync(dst, h_xyz, bytes, cudaMemcpyHostToDevice, c->s_copy));
+        } else {                                                     // raw bytes now, decode behind the copy on the main stream
+            // raw staging = a bump allocator over a modest device region: when it is full every earlier block has been
+            // (or is about to be) decoded — wait for that and start over
+            c->b_raw = (c->b_raw + 15) & ~(size_t)15;
+            if (c->b_raw + bytes > c->d_braw.cap) {
+                TG_CUDA(cudaStreamSynchronize(c->s_copy));
+                TG_CUDA(cudaStreamSynchronize(c->stream));
+                c->b_raw = 0;
+                int rc = c->d_braw.reserve(bytes);
+                if (rc) return rc;
+            }
+            char* raw = (char*)c->d_braw.p + c->b_raw;
+            TG_CUDA(cudaMemcpyAsync(raw, h_xyz, bytes, cudaMemcpyHostToDevice, c->s_copy));
+            TG_CUDA(cudaEventRecord(c->ev_push, c->s_copy));
+            TG_CUDA(cudaStreamWaitEvent(c->stream, c->ev_push, 0));
+            int rc = decode_points(c, raw, xyz_dtype, 3 * P_i, dst, c->stream);
+            if (rc) return rc;
+            c->b_raw += bytes;
+        }
+    }
+    c->b_P += P_i; c->b_S += S_i;
+    return TG_OK;
+}
+
+int tg_batch_run(tg_context* c, const int64_t* h_bo, int64_t B, double* h_out, uint8_t* h_keep, double* h_sums, int64_t* h_counts,
+                 double* h_spread) {
+    if (!c) return set_err(TG_E_INVALID, "null context");
+    if (c->b_Pcap < 0) return set_err(TG_E_INVALID, "tg_batch_run without tg_batch_begin");
+    if (B < 0 || (B > 0 && (!h_bo || !h_sums || !h_counts))) return set_err(TG_E_INVALID, "bad bundle argument");
+    const int64_t S = c->b_S, P = c->b_P;
+    c->b_Pcap = -1;                                                  // the batch is consumed whatever happens
+    if (S == 0) return TG_OK;
+    DeviceGuard g(c->device);
+    cudaStream_t st = c->stream;
+    auto body = [&]() -> int {
+        int rc;
+        if ((rc = c->d_off.reserve(sizeof(int64_t) * (size_t)(S + 1)))) return rc;
+        if ((rc = c->d_out.reserve(sizeof(double) * TG_N_METRICS * (size_t)S))) return rc;
+        if ((rc = c->d_keep.reserve((size_t)S))) return rc;
+        if ((rc = c->d_sums.reserve(sizeof(double) * tg::kNB * (size_t)B))) return rc;
+        if ((rc = c->d_counts.reserve(sizeof(int64_t) * (tg::kNB + 1) * (size_t)B))) return rc;
+        if (h_spread && (rc = c->d_spread.reserve(sizeof(double) * 3 * tg::kNB * (size_t)B))) return rc;
+        TG_CUDA(cudaMemcpyAsync(c->d_off.p, c->h_boff.p, sizeof(int64_t) * (size_t)(S + 1), cudaMemcpyHostToDevice, c->s_copy));
+        TG_CUDA(cudaEventRecord(c->ev_push, c->s_copy));             // every pushed copy precedes this event on s_copy
+        TG_CUDA(cudaStreamWaitEvent(st, c->ev_push, 0));
+        const double* d_pts = (const double*)((char*)c->d_bxyz.p + 256);
+        const uint64_t lo = (uint64_t)(uintptr_t)d_pts;
+        double* d_out = (double*)c->d_out.p;
+        uint8_t* d_keep = (uint8_t*)c->d_keep.p;
+        if ((rc = launch_metrics_f64(c, d_pts, lo - 32, lo + 24ull * (uint64_t)P + 32, (const int64_t*)c->d_off.p, S, d_out, S, d_keep, st))) return rc;
+        if (h_out) TG_CUDA(cudaMemcpyAsync(h_out, d_out, sizeof(double) * TG_N_METRICS * (size_t)S, cudaMemcpyDeviceToHost, st));
+        if (h_keep) TG_CUDA(cudaMemcpyAsync(h_keep, d_keep, (size_t)S, cudaMemcpyDeviceToHost, st));
+        if (B > 0) {
+            if ((rc = tg_bundle_reduce_dev(c, d_out, d_keep, nullptr, S, h_bo, B, (double*)c->d_sums.p, (int64_t*)c->d_counts.p, st))) return rc;
+            TG_CUDA(cudaMemcpyAsync(h_sums, c->d_sums.p, sizeof(double) * tg::kNB * (size_t)B, cudaMemcpyDeviceToHost, st));
+            TG_CUDA(cudaMemcpyAsync(h_counts, c->d_counts.p, sizeof(int64_t) * (tg::kNB + 1) * (size_t)B, cudaMemcpyDeviceToHost, st));
+            if (h_spread) {
+                if ((rc = tg_bundle_spread_dev(c, d_out, d_keep, nullptr, S, h_bo, B, (const double*)c->d_sums.p, (const int64_t*)c->d_counts.p,
+                                               (double*)c->d_spread.p, st))) return rc;
+                TG_CUDA(cudaMemcpyAsync(h_spread, c->d_spread.p, sizeof(double) * 3 * tg::kNB * (size_t)B, cudaMemcpyDeviceToHost, st));
+            }
+        }
+        TG_CUDA(cudaStreamSynchronize(st));
+        return TG_OK;
+    };
+    const int rc = body();
+    if (rc != TG_OK) drain_streams(c);
+    return rc;
+}
+
+int tg_batch_size(tg_context* c, int64_t* S, int64_t* P) {
+    if (!c || !S || !P) return set_err(TG_E_INVALID, "null argument");
+    *S = c->b_S; *P = c->b_P;
+    return TG_OK;
 }
 
 }  // extern "C"

@@ -78,19 +78,33 @@ def find_tract_file(data_dir, subject_id, timepoint, tract_name):
 def select_prefix(points, offsets, max_streamlines):
     """The loader rule of tract_geom_proc.py:17-25 on a CSR tractogram, vectorised: indices of the
     polylines with more than 2 points and only finite coordinates, in file order, cut after
-    ``max_streamlines`` of them (the cap is tested after an append, so a cap <= 0 still admits one)."""
+    ``max_streamlines`` of them (the cap is tested after an append, so a cap <= 0 still admits one).
+
+    With a cap only the candidates actually needed are inspected (a file of 5,000 polylines capped at 100 costs
+    100 polylines' worth of finite tests); points may be in the file's big-endian storage."""
     offsets = np.asarray(offsets, dtype=np.int64)
     n = np.diff(offsets)
-    S = len(n)
-    if S == 0:
+    if len(n) == 0:
         return np.zeros(0, dtype=np.int64)
-    bad_pt = ~np.isfinite(points).all(axis=1) if len(points) else np.zeros(0, bool)
-    csum = np.concatenate([[0], np.cumsum(bad_pt, dtype=np.int64)])
-    bad = (csum[offsets[1:]] - csum[offsets[:-1]]) > 0
-    idx = np.flatnonzero((n > 2) & ~bad)
-    if max_streamlines is not None:
-        idx = idx[:max(int(max_streamlines), 1)]
-    return idx
+    cand = np.flatnonzero(n > 2)
+    if max_streamlines is None:
+        want = len(cand)
+    else:
+        want = max(int(max_streamlines), 1)
+    keep = []
+    have, pos = 0, 0
+    while have < want and pos < len(cand):
+        take = cand[pos:pos + max(want - have, 64)]
+        pos += len(take)
+        lo, hi = int(offsets[take[0]]), int(offsets[take[-1] + 1])
+        block = np.asarray(points[lo:hi])
+        bad_pt = ~np.isfinite(block.astype(block.dtype.newbyteorder("="), copy=False)).all(axis=1)
+        csum = np.concatenate([[0], np.cumsum(bad_pt, dtype=np.int64)])
+        ok = (csum[offsets[take + 1] - lo] - csum[offsets[take] - lo]) == 0
+        good = take[ok][:want - have]
+        keep.append(good)
+        have += len(good)
+    return np.concatenate(keep) if keep else np.zeros(0, dtype=np.int64)
 
 
 def gather_polylines(points, offsets, idx):
@@ -106,47 +120,147 @@ def gather_polylines(points, offsets, idx):
 
 
 def _default_compute(points, offsets, bundle_offsets):
-    """One device call for the whole batch -> (n_streamlines int64[B], means float64[B,13])."""
+    """One device call for an in-memory batch -> (n_streamlines int64[B], means float64[B,13])."""
     from . import _lib
     ctx = _lib.default_context()
     _, _, sums, counts = ctx.metrics_host(points, offsets, bundle_offsets, want_rows=False)
+    return counts[:, 0].copy(), _means(sums, counts)
+
+
+def _means(sums, counts):
     with np.errstate(invalid="ignore", divide="ignore"):
-        means = np.where(counts[:, 1:] > 0, sums / np.maximum(counts[:, 1:], 1), np.nan)
-    return counts[:, 0].copy(), means
+        return np.where(counts[:, 1:] > 0, sums / np.maximum(counts[:, 1:], 1), np.nan)
+
+
+_DEVICE_COMPUTE = _default_compute          # process_batch streams files to the device unless this module attribute was replaced
+MAX_BATCH_POINTS = 1 << 27        # a device call is flushed beyond this many points (3.2 GB of float64 coordinates)
+
+
+def _load(path, max_streamlines, arena):
+    """One tract file -> (points, local offsets) of the polylines the reference's loader would hand over, or None.
+
+    ``max_streamlines=None``: the whole file as it is (the loader filter is evaluated on the device, `keep` flags);
+    otherwise the prefix rule (select_prefix).  Points stay in the file's storage type and — with an arena — in
+    pinned memory."""
+    pts, off = vtk_io.read_polylines_raw(path, arena)
+    if max_streamlines is None:
+        return (pts, off) if len(off) > 1 else None
+    idx = select_prefix(pts, off, max_streamlines)
+    if len(idx) == 0:
+        return None
+    return gather_polylines(pts, off, idx)
+
+
+def compute_files(paths, max_streamlines=None, ctx=None, arena=None, on_error=None):
+    """The files of a batch through ONE device call: -> (n_streamlines int64[F], means float64[F,13]), one bundle
+    per file; an unreadable or empty file gives n_streamlines 0 and NaN means (``on_error(i, exc)`` is told).
+
+    Pipeline (comprehensive_tract_geometry_analysis.py:169-195 is the serial loop replaced): file i
+    is parsed into pinned memory and PUSHED (tg_batch_push queues its host-to-device copy and returns), so parsing
+    file i+1 overlaps the transfer and decode of file i; tg_batch_run then computes every polyline and reduces the
+    bundles.  Batches are flushed at MAX_BATCH_POINTS points.  A device failure of a batch falls back to one call per
+    file, so that only the failing tracts are lost (the reference isolates failures per tract, :95-131)."""
+    from . import _lib
+    ctx = ctx or _lib.default_context()
+    if arena is None:
+        try:
+            arena = _lib.default_arena()
+        except _lib.TractGeomError:
+            arena = None                                   # no pinned memory: pageable copies, same results
+    F = len(paths)
+    n_sl = np.zeros(F, dtype=np.int64)
+    means = np.full((F, _lib.N_BUNDLE_COLS), np.nan)
+
+    def run(members, bo):
+        _, _, sums, counts = ctx.batch_run(np.asarray(bo, dtype=np.int64))
+        m = _means(sums, counts)
+        for b, i in enumerate(members):
+            n_sl[i], means[i] = counts[b, 0], m[b]
+
+    def one_by_one(members):
+        for i in members:
+            try:
+                item = _load(paths[i], max_streamlines, None)
+                if item is None:
+                    continue
+                _, _, sums, counts = ctx.metrics_host(item[0], item[1], want_rows=False)
+                n_sl[i], means[i] = counts[0, 0], _means(sums, counts)[0]
+            except Exception as e:
+                if on_error:
+                    on_error(i, e)
+
+    i = 0
+    while i < F:
+        if arena is not None:
+            arena.reset()
+        members, bo, pushed, held = [], [0], 0, []
+        try:
+            ctx.batch_begin(1 << 20, 1 << 14)
+            while i < F and pushed < MAX_BATCH_POINTS:
+                try:
+                    item = _load(paths[i], max_streamlines, arena)
+                except Exception as e:                      # the reference prints and skips (:129-131)
+                    if on_error:
+                        on_error(i, e)
+                    item = None
+                if item is not None:
+                    held.append(ctx.batch_push(item[0], item[1]))     # keeps the (pinned) array alive until the run
+                    members.append(i)
+                    bo.append(bo[-1] + len(item[1]) - 1)
+                    pushed += int(item[1][-1])
+                i += 1
+            if members:
+                run(members, bo)
+        except _lib.TractGeomError as e:                    # device-side failure of the batch: isolate it per file
+            if on_error:
+                on_error(-1, e)
+            one_by_one(members)
+        del held
+    return n_sl, means
 
 
 def process_batch(jobs, max_streamlines=None, compute: Optional[Callable] = None, verbose=False):
     """``jobs`` = list of (subject_id, timepoint, tract_name, group, path).  Returns one metrics dict per
     job, or None where the reference would have skipped the tract (unreadable file, :129-131, or no
-    surviving streamline, which raises KeyError('length') inside the reference's hot path)."""
-    compute = compute or _default_compute
-    P, O, B, live = [], [np.zeros(1, np.int64)], [0], []
-    base = 0
-    dtype = None
-    for j, (_, _, tract, _, path) in enumerate(jobs):
-        try:
-            pts, off = vtk_io.read_polylines_csr(path)
-        except Exception as e:  # the reference prints and skips (:129-131)
-            if verbose:
-                print(f"      [ERROR] Failed to process {tract}: {e}")
-            continue
-        idx = select_prefix(pts, off, max_streamlines)
-        if len(idx) == 0:
-            if verbose:
-                print(f"      [ERROR] Failed to process {tract}: 'length'")
-            continue
-        p, o = gather_polylines(pts, off, idx)
-        dtype = p.dtype if dtype is None else np.result_type(dtype, p.dtype)
-        P.append(p); O.append(o[1:] + base); base += int(o[-1]); B.append(B[-1] + len(idx)); live.append(j)
+    surviving streamline, which raises KeyError('length') inside the reference's hot path).
+
+    ``compute`` = a hook ``(points, offsets, bundle_offsets) -> (n_streamlines, means)`` for an in-memory batch
+    (the CPU tests plug the oracle in here); by default the files stream through :func:`compute_files`."""
     results = [None] * len(jobs)
-    if not live:
-        return results
-    points = np.concatenate([np.asarray(p, dtype=dtype) for p in P]) if len(P) > 1 else np.ascontiguousarray(P[0], dtype=dtype)
-    n_sl, means = compute(points, np.concatenate(O), np.asarray(B, dtype=np.int64))
+    errors = {}
+    if compute is None and _default_compute is not _DEVICE_COMPUTE:
+        compute = _default_compute                     # a test (or a caller) swapped the in-memory hook
+    if compute is None:
+        n_all, means_all = compute_files([j[4] for j in jobs], max_streamlines, on_error=lambda i, e: errors.__setitem__(i, e))
+        live = list(range(len(jobs)))
+        n_sl, means = n_all, means_all
+    else:
+        P, O, B, live = [], [np.zeros(1, np.int64)], [0], []
+        base = 0
+        dtype = None
+        for j, (_, _, tract, _, path) in enumerate(jobs):
+            try:
+                pts, off = vtk_io.read_polylines_csr(path)
+            except Exception as e:  # the reference prints and skips (:129-131)
+                errors[j] = e
+                continue
+            idx = select_prefix(pts, off, max_streamlines)
+            if len(idx) == 0:
+                continue
+            p, o = gather_polylines(pts, off, idx)
+            dtype = p.dtype if dtype is None else np.result_type(dtype, p.dtype)
+            P.append(p); O.append(o[1:] + base); base += int(o[-1]); B.append(B[-1] + len(idx)); live.append(j)
+        if live:
+            points = np.concatenate([np.asarray(p, dtype=dtype) for p in P]) if len(P) > 1 else np.ascontiguousarray(P[0], dtype=dtype)
+            n_sl, means = compute(points, np.concatenate(O), np.asarray(B, dtype=np.int64))
+        else:
+            n_sl, means = np.zeros(0, np.int64), np.zeros((0, 13))
     for b, j in enumerate(live):
         subject_id, timepoint, tract, group, _ = jobs[j]
-        if n_sl[b] == 0:                               # every selected polyline had length <= 1e-8
-            if verbose:
+        if j in errors and verbose:
+            print(f"      [ERROR] Failed to process {tract}: {errors[j]}")
+        if n_sl[b] == 0:                               # unreadable, nothing selected, or every selected polyline had length <= 1e-8
+            if verbose and j not in errors:
                 print(f"      [ERROR] Failed to process {tract}: 'length'")
             continue
         m = {"n_streamlines": float(n_sl[b])}          # Series.to_dict of a mixed int/float row gives floats (:109)

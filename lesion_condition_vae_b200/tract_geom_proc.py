@@ -130,16 +130,27 @@ def compute_streamline_metrics_csr(points, offsets, max_streamlines: Optional[in
     return frames_from_table(out, rows, sums, counts, None if spread is None else spread[0])
 
 
+def _load_for_device(vtk_path):
+    """ref:9-26 without the Python loop: the file's POINTS block lands in pinned memory in the file's own storage type
+    (big-endian float/double for binary files: the device swaps and upcasts), the cell array becomes CSR offsets."""
+    try:
+        arena = _lib.default_arena()
+        arena.reset()                                      # the previous call's views are dead: results were copied out
+    except _lib.TractGeomError:
+        arena = None                                       # no device: the call below raises anyway
+    return vtk_io.read_polylines_raw(vtk_path, arena)
+
+
 def compute_streamline_metrics(vtk_path: str, max_streamlines: Optional[int] = None) -> Tuple[pd.DataFrame, pd.DataFrame]:
     """Returns: df_sl (per streamline) and df_bundle (bundle-level summary).  Drop-in for ref:153."""
-    points, offsets = vtk_io.read_polylines_csr(vtk_path)
+    points, offsets = _load_for_device(vtk_path)
     return compute_streamline_metrics_csr(points, offsets, max_streamlines)
 
 
 def compute_streamline_metrics_extended(vtk_path: str, max_streamlines: Optional[int] = None) -> Tuple[pd.DataFrame, pd.DataFrame]:
     """:func:`compute_streamline_metrics` with the opt-in spread columns (``SPREAD_COLUMNS``) appended to
     df_bundle.  A separate name, so the drop-in keeps the reference's exact signature and schema."""
-    points, offsets = vtk_io.read_polylines_csr(vtk_path)
+    points, offsets = _load_for_device(vtk_path)
     return compute_streamline_metrics_csr(points, offsets, max_streamlines, extra_stats=True)
 
 

@@ -117,9 +117,9 @@ def _read_bytes(path):
         return f.read()
 
 
-def parse_legacy_polydata(buf: bytes):
-    """-> (points (P,3) native-endian float32/float64, offsets int64[S+1], connectivity int64[C])."""
-    cur = _Cursor(buf)
+def _parse_header(cur):
+    """Magic, title, ASCII|BINARY, DATASET POLYDATA -> True when the file is binary."""
+    buf = cur.b
     magic = cur.line()
     if magic is None or not magic.lower().startswith(b"# vtk datafile"):
         raise VTKFormatError("not a legacy VTK file")
@@ -129,12 +129,55 @@ def parse_legacy_polydata(buf: bytes):
     fmt = cur.line()
     if fmt is None or fmt.upper() not in (b"ASCII", b"BINARY"):
         raise VTKFormatError(f"expected ASCII or BINARY, got {fmt!r}")
-    binary = fmt.upper() == b"BINARY"
     ds = cur.line()
     if ds is None or ds.upper().split() != [b"DATASET", b"POLYDATA"]:
         raise VTKFormatError(f"only DATASET POLYDATA is supported, got {ds!r}")
+    return fmt.upper() == b"BINARY"
 
-    points = None
+
+def _skip_field(cur, tok, binary):
+    """FIELD <name> <numArrays>, then per array `<name> <numComponents> <numTuples> <type>` + data (vtkPolyDataWriter
+    puts such a block BEFORE the geometry when the data set carries field data)."""
+    try:
+        n_arrays = int(tok[2])
+    except (IndexError, ValueError) as e:
+        raise VTKFormatError("malformed FIELD header") from e
+    for _ in range(n_arrays):
+        ln = cur.line()
+        if ln is None:
+            raise VTKFormatError("truncated FIELD block")
+        t = ln.split()
+        try:
+            comps, tuples, typ = int(t[1]), int(t[2]), t[3].lower()
+        except (IndexError, ValueError) as e:
+            raise VTKFormatError(f"malformed FIELD array header {ln[:40]!r}") from e
+        count = comps * tuples
+        if typ == b"string":
+            for _ in range(count):                       # one (binary: length-prefixed-free, newline-terminated) line per string
+                j = cur.b.find(b"\n", cur.i)
+                cur.i = (j + 1) if j >= 0 else len(cur.b)
+            continue
+        if typ == b"bit":
+            if binary:
+                cur.i += (count + 7) // 8
+            else:
+                cur.ascii(">i4", count)
+            continue
+        dt = _VTK_TYPES.get(typ)
+        if dt is None:
+            raise VTKFormatError(f"unknown FIELD array type {t[3]!r}")
+        if binary:
+            cur.binary(dt, count)
+        else:
+            cur.ascii(dt if np.dtype(dt).kind == "f" else ">i8", count)
+
+
+def _parse_sections(cur, binary, points=None, keep_order=False):
+    """Sections after the header -> (points (P,3), offsets int64[S+1], connectivity int64[C]).
+
+    ``points`` given: the POINTS block was already consumed by the caller (streaming reader).  ``keep_order``: binary
+    points stay in the file's big-endian byte order (a zero-copy view; the device swaps them), else native-endian."""
+    buf = cur.b
     offsets = None
     conn = None
     while True:
@@ -151,7 +194,9 @@ def parse_legacy_polydata(buf: bytes):
             flat = cur.binary(dt, 3 * n) if binary else cur.ascii(dt, 3 * n)
             if flat.dtype.kind != "f":
                 flat = flat.astype(np.float64)
-            points = flat.astype(flat.dtype.newbyteorder("="), copy=False).reshape(n, 3)
+            if not (keep_order and binary):
+                flat = flat.astype(flat.dtype.newbyteorder("="), copy=False)
+            points = flat.reshape(n, 3)
         elif key == b"METADATA":
             # INFORMATION block, terminated by a blank line
             while True:
@@ -182,12 +227,12 @@ def parse_legacy_polydata(buf: bytes):
                 flat = cur.binary(">i4", b) if binary else cur.ascii(">i4", b)
                 if key == b"LINES":
                     offsets, conn = legacy_lines_to_csr(flat.astype(np.int64), a)
-        elif key in (b"POINT_DATA", b"CELL_DATA", b"FIELD"):
+        elif key == b"FIELD":
             if points is not None and offsets is not None:
                 break          # geometry complete; attributes are not used by this path
-            if key == b"FIELD":
-                raise VTKFormatError("FIELD data before the geometry is not supported")
-            break
+            _skip_field(cur, tok, binary)                                    # field data in front of the geometry
+        elif key in (b"POINT_DATA", b"CELL_DATA"):
+            break              # attributes follow the geometry and are not used by this path
         else:
             raise VTKFormatError(f"unsupported section {ln[:40]!r}")
     if points is None:
@@ -196,6 +241,14 @@ def parse_legacy_polydata(buf: bytes):
         offsets = np.zeros(1, dtype=np.int64)
         conn = np.empty(0, dtype=np.int64)
     return points, offsets, conn
+
+
+def parse_legacy_polydata(buf: bytes, keep_order=False):
+    """-> (points (P,3) float32/float64 — native-endian, or the file's big-endian order with ``keep_order`` —,
+    offsets int64[S+1], connectivity int64[C])."""
+    cur = _Cursor(buf)
+    binary = _parse_header(cur)
+    return _parse_sections(cur, binary, keep_order=keep_order)
 
 
 def legacy_lines_to_csr(lines, n_cells=None):
@@ -227,15 +280,13 @@ def legacy_lines_to_csr(lines, n_cells=None):
             return native.vtk_lines_to_csr(lines)
         except native.TractGeomError as e:
             raise VTKFormatError("corrupt LINES array") from e
-    lst = lines.tolist() if L < (1 << 26) else None
-    if lst is not None:
-        while i < L:
-            heads.append(i)
-            i += 1 + lst[i]
-    else:
-        while i < L:
-            heads.append(i)
-            i += 1 + int(lines[i])
+    lst = lines.tolist() if L < (1 << 26) else lines
+    while i < L:
+        n = int(lst[i])
+        if n < 0 or i + 1 + n > L:                    # checked INSIDE the walk: a negative count would never advance
+            raise VTKFormatError("corrupt LINES array")
+        heads.append(i)
+        i += 1 + n
     h = np.asarray(heads, dtype=np.int64)
     counts = lines[h]
     if counts.min(initial=0) < 0 or (h[-1] + 1 + counts[-1]) > L:
@@ -246,20 +297,90 @@ def legacy_lines_to_csr(lines, n_cells=None):
     return offsets, lines[mask]
 
 
+def _apply_connectivity(pts, off, conn):
+    if conn.size and (conn.min() < 0 or conn.max() >= len(pts)):
+        raise VTKFormatError("LINES connectivity refers to a point that does not exist")
+    identity = conn.size == len(pts) and (conn.size == 0 or (conn[0] == 0 and conn[-1] == conn.size - 1 and np.all(np.diff(conn) == 1)))
+    return pts if identity else pts[conn]                   # tract_geom_proc.py:19-20 in one gather
+
+
 def read_polylines_csr(path, dtype=None):
-    """File -> (points_csr (C,3), offsets int64[S+1]) with the connectivity already applied.
+    """File -> (points_csr (C,3), offsets int64[S+1]) with the connectivity already applied, native byte order.
 
     ``dtype=None`` keeps the file's point dtype (float32 for the usual ``POINTS n float``);
     pass np.float64 for the canonical parity input (exact upcast).
     """
     pts, off, conn = _read_any(path)
-    if conn.size and (conn.min() < 0 or conn.max() >= len(pts)):
-        raise VTKFormatError("LINES connectivity refers to a point that does not exist")
-    identity = conn.size == len(pts) and (conn.size == 0 or (conn[0] == 0 and conn[-1] == conn.size - 1 and np.all(np.diff(conn) == 1)))
-    out = pts if identity else pts[conn]                    # tract_geom_proc.py:19-20 in one gather
+    out = _apply_connectivity(pts, off, conn)
     if dtype is not None:
         out = out.astype(dtype, copy=False)
     return np.ascontiguousarray(out), off
+
+
+def read_polylines_raw(path, arena=None):
+    """File -> (points (C,3), offsets int64[S+1]) for the device path: no per-point work on the host.
+
+    Binary legacy files keep their big-endian ``float``/``double`` bytes (the device swaps and upcasts them,
+    tg_dtype TG_F32_BE / TG_F64_BE).  With ``arena`` (a ``_lib.PinnedArena``) the POINTS block of an uncompressed
+    file is read from the file STRAIGHT into pinned memory (``readinto``; a .vtk.gz block is copied there after
+    the in-memory gunzip), so the host-to-device copy that follows is an asynchronous DMA transfer."""
+    p = os.fspath(path)
+    low = p.lower()
+    if not (low.endswith(".vtk") or low.endswith(".vtk.gz")):
+        return read_polylines_csr(p)
+    if not os.path.exists(p):
+        raise FileNotFoundError(p)
+    with open(p, "rb") as f:
+        head = f.read(1 << 16)
+        hit = None if head[:2] == b"\x1f\x8b" else _leading_points_block(head)
+        if hit is None:                                     # gzip, ASCII, or something in front of POINTS: whole-buffer parse
+            buf = head + f.read()
+            if buf[:2] == b"\x1f\x8b":
+                buf = gzip.decompress(buf)
+            pts, off, conn = parse_legacy_polydata(buf, keep_order=True)
+            out = _apply_connectivity(pts, off, conn)
+            if arena is not None and out.size:
+                pinned = arena.take(out.nbytes).view(out.dtype).reshape(out.shape)
+                np.copyto(pinned, out)
+                out = pinned
+            return np.ascontiguousarray(out), off
+        n, dt, start = hit
+        nbytes = 3 * n * np.dtype(dt).itemsize
+        block = arena.take(nbytes) if arena is not None else np.empty(nbytes, dtype=np.uint8)
+        have = min(len(head) - start, nbytes)
+        block[:have] = np.frombuffer(head, dtype=np.uint8, count=have, offset=start)
+        if have < nbytes:
+            got = f.readinto(memoryview(block)[have:])
+            if got != nbytes - have:
+                raise VTKFormatError("truncated binary block")
+            rest = f.read()
+        else:
+            rest = head[start + nbytes:] + f.read()
+    pts = block.view(dt).reshape(n, 3)
+    _, off, conn = _parse_sections(_Cursor(rest), True, points=pts, keep_order=True)
+    out = _apply_connectivity(pts, off, conn)
+    return (out if out.flags.c_contiguous else np.ascontiguousarray(out)), off
+
+
+def _leading_points_block(head: bytes):
+    """(n, big-endian dtype, byte offset of the data) when ``head`` starts a BINARY POLYDATA file whose first section is
+    POINTS with a float type; None otherwise (the caller then parses the whole buffer)."""
+    try:
+        cur = _Cursor(head)
+        if not _parse_header(cur):
+            return None
+        ln = cur.line()
+        if ln is None:
+            return None
+        tok = ln.split()
+        if tok[0].upper() != b"POINTS":
+            return None
+        dt = _VTK_TYPES.get(tok[2].lower())
+        if dt is None or np.dtype(dt).kind != "f" or cur.i > len(head):
+            return None
+        return int(tok[1]), dt, cur.i
+    except (VTKFormatError, IndexError, ValueError):
+        return None
 
 
 def _read_any(path):

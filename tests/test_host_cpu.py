@@ -194,3 +194,83 @@ def test_new_entry_points_reject_a_null_context_without_touching_cuda():
     assert lib.tg_resample_csr_dev(None, None, 0, None, 0, 0, 100, None, None) == -1
     assert lib.tg_resample_csr_host(None, None, 0, None, 0, 0, 100, None) == -1
     assert b"null context" in lib.tg_last_error()
+
+
+# ---- reader hardening: byte-level fixtures written WITHOUT this package's writer ------------------------
+VTK_FIXTURES = os.path.join(ROOT, "tests", "golden", "vtk")
+
+
+@pytest.mark.parametrize("name,case", [("v42_field_float.vtk", "v42_field_float"), ("v51_offsets.vtk", "v51_offsets"),
+                                       ("v51_offsets.vtk.gz", "v51_offsets"), ("v30_ascii_field.vtk", "v30_ascii_field")])
+def test_reader_on_vtkpolydatawriter_layouts(name, case):
+    """FIELD data in front of the geometry (v4.2 binary float, and ASCII), v5.1 OFFSETS / CONNECTIVITY vtktypeint64 with a
+    METADATA block, the same gzipped, trailing CELL_DATA / POINT_DATA, and a connectivity that is not the identity."""
+    exp = np.load(os.path.join(VTK_FIXTURES, "expected.npz"))
+    pts, off = vtk_io.read_polylines_csr(os.path.join(VTK_FIXTURES, name), dtype=np.float64)
+    assert np.array_equal(off, exp[case + "/offsets"]) and np.array_equal(pts, exp[case + "/points"])
+    # the device-path reader: same values, binary files left in the file's big-endian storage (no per-point host work)
+    raw, off2 = vtk_io.read_polylines_raw(os.path.join(VTK_FIXTURES, name))
+    assert np.array_equal(off2, off) and np.array_equal(raw.astype(np.float64), pts)
+    if not name.startswith("v30"):
+        assert raw.dtype.byteorder == ">" and _lib.dtype_code(raw) in (_lib.F32_BE, _lib.F64_BE)
+
+
+def test_raw_reader_streams_the_points_block_into_a_given_buffer(tmp_path):
+    """read_polylines_raw(arena=...) reads the POINTS block of an uncompressed binary file straight into the arena (readinto),
+    larger than the 64 KB header probe, and copies a gunzipped block into it."""
+    class Arena:                                           # stands in for _lib.PinnedArena (which needs a CUDA device)
+        def __init__(self):
+            self.blocks = []
+
+        def take(self, nbytes, dtype=np.uint8):
+            self.blocks.append(np.zeros(nbytes, dtype=np.uint8))
+            return self.blocks[-1].view(dtype)
+
+    pts, off = synth.random_walk_csr(synth.lengths_uniform(np.random.default_rng(3), 400, 3, 90), 8)
+    for gz, pd_ in ((False, "float"), (False, "double"), (True, "float")):
+        p = vtk_io.write_polylines(tmp_path / ("a.vtk.gz" if gz else f"a_{pd_}.vtk"), pts, off, binary=True, point_dtype=pd_)
+        ar = Arena()
+        raw, o = vtk_io.read_polylines_raw(p, ar)
+        ref, o_ref = vtk_io.read_polylines_csr(p)
+        assert np.array_equal(o, o_ref) and np.array_equal(raw.astype(ref.dtype), ref)
+        assert len(ar.blocks) == 1 and np.shares_memory(raw, ar.blocks[0]) and ar.blocks[0].nbytes == ref.nbytes > (1 << 16)
+
+
+def test_corrupt_cell_array_is_rejected_not_looped_on(monkeypatch):
+    """a negative cell count never advanced the numpy fallback walk.  Both walks (native helper, numpy) reject it."""
+    bad = np.array([3, 0, 1, 2, -1, 5, 6], dtype=np.int64)
+    with pytest.raises(vtk_io.VTKFormatError):
+        vtk_io.legacy_lines_to_csr(bad)
+    monkeypatch.setattr(vtk_io, "_NATIVE", None)
+    with pytest.raises(vtk_io.VTKFormatError):
+        vtk_io.legacy_lines_to_csr(bad)
+    with pytest.raises(vtk_io.VTKFormatError):
+        vtk_io.legacy_lines_to_csr(np.array([2, 0, 1, 4, 2], dtype=np.int64))       # last count overruns
+    off, conn = vtk_io.legacy_lines_to_csr(np.array([2, 0, 1, 3, 2, 3, 4], dtype=np.int64))
+    assert off.tolist() == [0, 2, 5] and conn.tolist() == [0, 1, 2, 3, 4]
+
+
+def test_select_prefix_matches_the_reference_loader_rule():
+    """The lazy prefix scan == the loader loop of tract_geom_proc.py:17-25, on native and on big-endian storage."""
+    from lesion_condition_vae_b200 import tract_driver as td
+    rng = np.random.default_rng(12)
+    for trial in range(30):
+        n = rng.integers(0, 7, size=rng.integers(1, 60))
+        pts, off = synth.random_walk_csr(np.maximum(n, 1), 100 + trial)
+        off = np.concatenate([[0], np.cumsum(np.maximum(n, 1))]).astype(np.int64)
+        for s in rng.integers(0, len(n), size=3):
+            if rng.random() < 0.5 and off[s + 1] > off[s]:
+                pts[off[s] + rng.integers(0, off[s + 1] - off[s]), rng.integers(0, 3)] = [np.nan, np.inf][trial % 2]
+        for ms in (None, 1, 3, 10, 0):
+            want = []
+            for s in range(len(n)):
+                sl = pts[off[s]:off[s + 1]]
+                if sl.shape[0] > 2 and np.isfinite(sl).all():
+                    want.append(s)
+                    if ms is not None and len(want) >= ms:
+                        break
+            for view in (pts, pts.astype(">f8"), pts.astype(">f4")):
+                ref = want if view.dtype.itemsize == 8 else None
+                got = td.select_prefix(view, off, ms).tolist()
+                if ref is not None:
+                    assert got == ref, (trial, ms)

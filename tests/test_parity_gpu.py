@@ -610,3 +610,65 @@ def test_coordinate_units(gpu_ctx, scale):
         ATOL.update(saved)
     bad = {k: v for k, v in errs.items() if not v <= 1.0}
     assert not bad, (scale, bad)
+
+
+def test_big_endian_storage_and_batch_api_are_bit_identical(gpu_ctx, tmp_path):
+    """The file's own storage (big-endian float / double, decoded on the device) gives the same bits as native arrays; a batch
+    pushed file by file (tg_batch_push / tg_batch_run, mixed storage types, pinned arena, capacity growth) gives the same
+    table and bundle sums as one tg_metrics_csr_host call on the concatenated tractogram."""
+    rng = np.random.default_rng(77)
+    files = []
+    for k in range(7):
+        n = synth.lengths_uniform(rng, 300 + 211 * k, 2, 130)
+        pts, off = synth.random_walk_csr(n, 500 + k)
+        if k == 3:
+            pts[off[5] + 1, 2] = np.nan
+        files.append((pts.astype(np.float32) if k % 2 else pts, off))
+    arena = _lib.PinnedArena(1 << 16)                          # small: must grow
+    gpu_ctx.batch_begin(1000, 10)                              # capacities are hints: must grow
+    held, cat_p, cat_o, bo = [], [], [np.zeros(1, np.int64)], [0]
+    base = 0
+    for k, (pts, off) in enumerate(files):
+        be = pts.astype(pts.dtype.newbyteorder(">")) if k % 3 else pts
+        pinned = arena.take(be.nbytes).view(be.dtype).reshape(be.shape)
+        np.copyto(pinned, be)
+        held.append(gpu_ctx.batch_push(pinned, off))
+        native64 = pts.astype(np.float64)
+        o1 = gpu_ctx.metrics_host(native64, off)
+        o2 = gpu_ctx.metrics_host(be, off)
+        assert np.array_equal(o1[0].view(np.uint64), o2[0].view(np.uint64)) and np.array_equal(o1[1], o2[1])
+        cat_p.append(native64); cat_o.append(off[1:] + base); base += int(off[-1]); bo.append(bo[-1] + len(off) - 1)
+    out, keep, sums, counts = gpu_ctx.batch_run(np.asarray(bo), want_rows=True)
+    ref = gpu_ctx.metrics_host(np.concatenate(cat_p), np.concatenate(cat_o), np.asarray(bo))
+    assert np.array_equal(out.view(np.uint64), ref[0].view(np.uint64)) and np.array_equal(keep, ref[1])
+    assert np.array_equal(counts, ref[3]) and np.allclose(sums, ref[2], rtol=1e-13, atol=0)
+    assert (keep != 3).any()
+    arena.close()
+
+
+def test_compute_files_streams_a_study_like_the_per_file_calls(gpu_ctx, tmp_path):
+    """tract_driver.compute_files (parse into pinned memory -> push -> one run) against compute_streamline_metrics file by file,
+    with and without the max_streamlines prefix rule, across binary/ASCII, float/double, gz, and an empty result."""
+    from lesion_condition_vae_b200 import tract_driver as td
+    rng = np.random.default_rng(5)
+    paths = []
+    for k in range(9):
+        pts, off = synth.random_walk_csr(synth.lengths_uniform(rng, 120 + 40 * k, 2, 60), 900 + k)
+        if k == 4:
+            pts, off = synth.lines_to_csr([np.zeros((2, 3)), np.ones((5, 3))])          # nothing survives
+        if k == 6:
+            pts[off[1] + 1, 0] = np.inf
+        paths.append(vtk_io.write_polylines(tmp_path / f"t{k}.vtk{'.gz' if k % 3 == 0 else ''}", pts, off, binary=(k % 4 != 1),
+                                            point_dtype="float" if k % 2 else "double", layout="offsets" if k == 5 else "classic"))
+    paths.append(str(tmp_path / "missing.vtk"))
+    for ms in (None, 25):
+        errors = {}
+        n_sl, means = td.compute_files(paths, ms, ctx=gpu_ctx, on_error=lambda i, e: errors.__setitem__(i, e))
+        assert set(errors) == {len(paths) - 1} and n_sl[-1] == 0 and n_sl[4] == 0
+        for i, p in enumerate(paths[:-1]):
+            if i == 4:
+                continue
+            _, df_b = tgp.compute_streamline_metrics(p, ms)
+            row = df_b.iloc[0].to_numpy(float)
+            assert n_sl[i] == row[0]
+            assert np.allclose(means[i], row[1:], rtol=1e-13, atol=0, equal_nan=True), (i, ms)
