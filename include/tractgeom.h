@@ -176,6 +176,10 @@ int tg_resample_csr_host(tg_context* ctx, const void* h_xyz, int xyz_dtype, cons
  *                        doubles); *consumed = bytes read; TG_E_INVALID when the text ends or is malformed. */
 int tg_vtk_lines_to_csr(const int64_t* lines, int64_t L, int64_t* offsets, int64_t* conn,
                         int64_t* n_cells, int64_t* n_conn);
+/*   tg_vtk_cells_be32_to_csr: the same walk on the cell array AS THE BINARY FILE HOLDS IT (L big-endian int32), one pass, no
+ *                        widened copy; *identity = 1 when the connectivity is 0,1,2,... (conn is then not written). */
+int tg_vtk_cells_be32_to_csr(const void* cells_be, int64_t L, int64_t* offsets, int64_t* conn,
+                             int64_t* n_cells, int64_t* n_conn, int* identity);
 int tg_parse_ascii_f64(const char* text, int64_t len, int64_t want, double* out, int64_t* consumed);
 int tg_parse_ascii_i64(const char* text, int64_t len, int64_t want, int64_t* out, int64_t* consumed);
 

@@ -21,7 +21,7 @@ EXPORTS = (
     "tg_metrics_csr_host", "tg_launch_count", "tg_bundle_spread_dev", "tg_metrics_csr_host_ex",
     "tg_resample_csr_dev", "tg_resample_csr_host", "tg_bundle_partials_dev",
     "tg_batch_begin", "tg_batch_push", "tg_batch_run", "tg_batch_size",
-    "tg_vtk_lines_to_csr", "tg_parse_ascii_f64", "tg_parse_ascii_i64",
+    "tg_vtk_lines_to_csr", "tg_vtk_cells_be32_to_csr", "tg_parse_ascii_f64", "tg_parse_ascii_i64",
 )
 
 
@@ -68,6 +68,7 @@ def load():
     lib.tg_resample_csr_dev.argtypes = [vp, vp, i32, vp, i64, i64, i32, vp, vp]
     lib.tg_resample_csr_host.argtypes = [vp, vp, i32, vp, i64, i64, i32, vp]
     lib.tg_vtk_lines_to_csr.argtypes = [vp, i64, vp, vp, C.POINTER(i64), C.POINTER(i64)]
+    lib.tg_vtk_cells_be32_to_csr.argtypes = [vp, i64, vp, vp, C.POINTER(i64), C.POINTER(i64), C.POINTER(i32)]
     lib.tg_parse_ascii_f64.argtypes = [C.c_char_p, i64, i64, vp, C.POINTER(i64)]
     lib.tg_parse_ascii_i64.argtypes = [C.c_char_p, i64, i64, vp, C.POINTER(i64)]
     lib.tg_metrics_csr_host_ex.argtypes = [vp, vp, i32, vp, i64, i64, vp, i64, vp, vp, vp, vp, vp]
@@ -260,6 +261,8 @@ class PinnedArena:
     reset must not be used afterwards."""
 
     def __init__(self, nbytes=1 << 20):
+        import threading
+        self._lock = threading.Lock()          # take() is called from the loader's parser threads
         self._lib = load()
         self._blocks = []          # (pointer, capacity, ctypes array); older blocks stay alive until close(): views point into them
         self._cap = 0
@@ -274,20 +277,26 @@ class PinnedArena:
         self._cap, self._used = cap, 0
 
     def reset(self):
-        """Recycle: keep only the newest (largest) block."""
-        for p, _, _ in self._blocks[:-1]:
-            self._lib.tg_host_free(p)
-        self._blocks = self._blocks[-1:]
-        self._used = 0
+        """Recycle.  If the last round needed several blocks, they are replaced by ONE block of their total size, so that
+        the same workload fits without another (slow) pinned allocation next time."""
+        with self._lock:
+            if len(self._blocks) > 1:
+                total = sum(cap for _, cap, _ in self._blocks)
+                for p, _, _ in self._blocks:
+                    self._lib.tg_host_free(p)
+                self._blocks, self._cap = [], 0
+                self._grow(total)
+            self._used = 0
 
     def take(self, nbytes, dtype=np.uint8):
         """A pinned array of ``nbytes`` bytes viewed as ``dtype`` (64-byte aligned)."""
-        start = (self._used + 63) & ~63
-        if start + nbytes > self._cap:
-            self._grow(nbytes + 64)
-            start = 0
-        self._used = start + int(nbytes)
-        raw = np.frombuffer(self._blocks[-1][2], dtype=np.uint8, count=int(nbytes), offset=start)
+        with self._lock:
+            start = (self._used + 63) & ~63
+            if start + nbytes > self._cap:
+                self._grow(nbytes + 64)
+                start = 0
+            self._used = start + int(nbytes)
+            raw = np.frombuffer(self._blocks[-1][2], dtype=np.uint8, count=int(nbytes), offset=start)
         return raw.view(dtype)
 
     def close(self):
@@ -325,6 +334,25 @@ def vtk_lines_to_csr(lines):
     ns, nc = C.c_int64(), C.c_int64()
     check(lib.tg_vtk_lines_to_csr(_ptr(lines), L, _ptr(offsets), _ptr(conn), C.byref(ns), C.byref(nc)))
     return offsets[:ns.value + 1].copy(), conn[:nc.value].copy()
+
+
+def vtk_cells_be32_to_csr(cells):
+    """Big-endian int32 classic cell array (as read from a binary file) -> (offsets int64[S+1], connectivity int64[C] or
+    None when it is the identity).  One native pass; raises TractGeomError on a corrupt array."""
+    lib = load()
+    cells = np.ascontiguousarray(cells)
+    assert cells.dtype.itemsize == 4
+    L = cells.size
+    offsets = np.empty(L + 1, dtype=np.int64)
+    ns, nc, ident = C.c_int64(), C.c_int64(), C.c_int()
+    conn = None
+    rc = lib.tg_vtk_cells_be32_to_csr(_ptr(cells), L, _ptr(offsets), None, C.byref(ns), C.byref(nc), C.byref(ident))
+    if rc != 0 and b"not the identity" in lib.tg_last_error():
+        conn = np.empty(max(L, 1), dtype=np.int64)
+        rc = lib.tg_vtk_cells_be32_to_csr(_ptr(cells), L, _ptr(offsets), _ptr(conn), C.byref(ns), C.byref(nc), C.byref(ident))
+    check(rc)
+    offsets = offsets[:ns.value + 1].copy()
+    return offsets, (None if ident.value else conn[:nc.value].copy())
 
 
 def parse_ascii(buf, start, count, integer=False):

@@ -989,6 +989,44 @@ int tg_vtk_lines_to_csr(const int64_t* lines, int64_t L, int64_t* offsets, int64
     return TG_OK;
 }
 
+// The classic binary cell array as the file holds it (big-endian int32 `[n, i0..i(n-1), n, ...]`) -> CSR offsets in ONE
+// pass, no widened copy; *identity = 1 when the connectivity is 0, 1, 2, ... (the usual tractography export: the points
+// are used as they are and `conn` is not written), else conn (capacity L) receives the point indices.
+int tg_vtk_cells_be32_to_csr(const void* cells_be, int64_t L, int64_t* offsets, int64_t* conn, int64_t* n_cells, int64_t* n_conn,
+                             int* identity) {
+    if (L < 0 || (L > 0 && !cells_be) || !offsets || !n_cells || !n_conn || !identity) return set_err(TG_E_INVALID, "null argument");
+    const uint32_t* w = (const uint32_t*)cells_be;
+    auto rd = [&](int64_t i) -> int64_t { return (int64_t)(int32_t)__builtin_bswap32(w[i]); };
+    int64_t i = 0, s = 0, c = 0;
+    bool ident = true;
+    offsets[0] = 0;
+    while (i < L) {
+        const int64_t n = rd(i);
+        if (n < 0 || n > L - i - 1) return set_err(TG_E_INVALID, "corrupt LINES array");
+        if (ident) {
+            for (int64_t k = 0; k < n; ++k)
+                if (rd(i + 1 + k) != c + k) { ident = false; break; }
+        }
+        c += n;
+        offsets[++s] = c;
+        i += 1 + n;
+    }
+    if (!ident) {
+        if (!conn) return set_err(TG_E_INVALID, "connectivity is not the identity and no buffer was given");
+        i = 0; c = 0;
+        while (i < L) {
+            const int64_t n = rd(i);
+            for (int64_t k = 0; k < n; ++k) conn[c + k] = rd(i + 1 + k);
+            c += n;
+            i += 1 + n;
+        }
+    }
+    *n_cells = s;
+    *n_conn = c;
+    *identity = ident ? 1 : 0;
+    return TG_OK;
+}
+
 static inline const char* skip_space(const char* p, const char* end) {
     while (p < end && (*p == ' ' || *p == '\n' || *p == '\t' || *p == '\r' || *p == '\f' || *p == '\v')) ++p;
     return p;
@@ -1203,6 +1241,9 @@ int tg_batch_begin(tg_context* c, int64_t P_cap, int64_t S_cap) {
     if ((rc = c->d_braw.reserve(std::min<size_t>(24 * (size_t)P_cap + 512, (size_t)64 << 20)))) return rc;
     if ((rc = c->d_bxyz.reserve(24 * (size_t)P_cap + 1024))) return rc;
     if ((rc = c->h_boff.reserve(sizeof(int64_t) * (size_t)(S_cap + 1)))) return rc;
+    // the scratch is grow-only: a new batch starts with whatever capacity earlier batches left behind
+    P_cap = std::max<int64_t>(P_cap, ((int64_t)c->d_bxyz.cap - 1024) / 24);
+    S_cap = std::max<int64_t>(S_cap, (int64_t)(c->h_boff.cap / sizeof(int64_t)) - 1);
     c->b_P = 0; c->b_S = 0; c->b_raw = 0; c->b_Pcap = P_cap; c->b_Scap = S_cap;
     ((int64_t*)c->h_boff.p)[0] = 0;
     return TG_OK;

@@ -172,7 +172,7 @@ def _skip_field(cur, tok, binary):
             cur.ascii(dt if np.dtype(dt).kind == "f" else ">i8", count)
 
 
-def _parse_sections(cur, binary, points=None, keep_order=False):
+def _parse_sections(cur, binary, points=None, keep_order=False, lazy_identity=False):
     """Sections after the header -> (points (P,3), offsets int64[S+1], connectivity int64[C]).
 
     ``points`` given: the POINTS block was already consumed by the caller (streaming reader).  ``keep_order``: binary
@@ -226,7 +226,14 @@ def _parse_sections(cur, binary, points=None, keep_order=False):
             else:                                                            # classic: a cells, b ints
                 flat = cur.binary(">i4", b) if binary else cur.ascii(">i4", b)
                 if key == b"LINES":
-                    offsets, conn = legacy_lines_to_csr(flat.astype(np.int64), a)
+                    native = _native() if binary else None
+                    if native is not None:                                   # one native pass over the file's own bytes
+                        try:
+                            offsets, conn = native.vtk_cells_be32_to_csr(flat)
+                        except native.TractGeomError as e:
+                            raise VTKFormatError("corrupt LINES array") from e
+                    else:
+                        offsets, conn = legacy_lines_to_csr(flat.astype(np.int64), a)
         elif key == b"FIELD":
             if points is not None and offsets is not None:
                 break          # geometry complete; attributes are not used by this path
@@ -240,15 +247,17 @@ def _parse_sections(cur, binary, points=None, keep_order=False):
     if offsets is None:
         offsets = np.zeros(1, dtype=np.int64)
         conn = np.empty(0, dtype=np.int64)
+    if conn is None and not lazy_identity:                 # the native cell walk reports an identity connectivity as None
+        conn = np.arange(int(offsets[-1]), dtype=np.int64)
     return points, offsets, conn
 
 
-def parse_legacy_polydata(buf: bytes, keep_order=False):
+def parse_legacy_polydata(buf: bytes, keep_order=False, lazy_identity=False):
     """-> (points (P,3) float32/float64 — native-endian, or the file's big-endian order with ``keep_order`` —,
     offsets int64[S+1], connectivity int64[C])."""
     cur = _Cursor(buf)
     binary = _parse_header(cur)
-    return _parse_sections(cur, binary, keep_order=keep_order)
+    return _parse_sections(cur, binary, keep_order=keep_order, lazy_identity=lazy_identity)
 
 
 def legacy_lines_to_csr(lines, n_cells=None):
@@ -298,6 +307,12 @@ def legacy_lines_to_csr(lines, n_cells=None):
 
 
 def _apply_connectivity(pts, off, conn):
+    if conn is None:                                        # the native cell walk found the identity
+        if int(off[-1]) != len(pts):
+            if int(off[-1]) > len(pts):
+                raise VTKFormatError("LINES connectivity refers to a point that does not exist")
+            return pts[:int(off[-1])]
+        return pts
     if conn.size and (conn.min() < 0 or conn.max() >= len(pts)):
         raise VTKFormatError("LINES connectivity refers to a point that does not exist")
     identity = conn.size == len(pts) and (conn.size == 0 or (conn[0] == 0 and conn[-1] == conn.size - 1 and np.all(np.diff(conn) == 1)))
@@ -337,7 +352,7 @@ def read_polylines_raw(path, arena=None):
             buf = head + f.read()
             if buf[:2] == b"\x1f\x8b":
                 buf = gzip.decompress(buf)
-            pts, off, conn = parse_legacy_polydata(buf, keep_order=True)
+            pts, off, conn = parse_legacy_polydata(buf, keep_order=True, lazy_identity=True)
             out = _apply_connectivity(pts, off, conn)
             if arena is not None and out.size:
                 pinned = arena.take(out.nbytes).view(out.dtype).reshape(out.shape)
@@ -357,7 +372,7 @@ def read_polylines_raw(path, arena=None):
         else:
             rest = head[start + nbytes:] + f.read()
     pts = block.view(dt).reshape(n, 3)
-    _, off, conn = _parse_sections(_Cursor(rest), True, points=pts, keep_order=True)
+    _, off, conn = _parse_sections(_Cursor(rest), True, points=pts, keep_order=True, lazy_identity=True)
     out = _apply_connectivity(pts, off, conn)
     return (out if out.flags.c_contiguous else np.ascontiguousarray(out)), off
 
@@ -389,7 +404,7 @@ def _read_any(path):
     if low.endswith(".vtk") or low.endswith(".vtk.gz"):
         if not os.path.exists(p):
             raise FileNotFoundError(p)
-        return parse_legacy_polydata(_read_bytes(p))
+        return parse_legacy_polydata(_read_bytes(p), lazy_identity=True)
     try:
         import pyvista as pv   # optional: other formats
     except ImportError as e:
