@@ -52,6 +52,9 @@
 
 namespace tg {
 
+#ifndef TG_STAGE_BULK
+#define TG_STAGE_BULK 0      // 1: experiment — stage with per-lane TMA bulk copies (cp.async.bulk + mbarrier) instead of cp.async pieces
+#endif
 #ifndef TG_OUT_EVICT_LAST
 #define TG_OUT_EVICT_LAST 1
 #endif
@@ -75,7 +78,7 @@ constexpr int kSlotBytes = kChunkBytes + 32;  // one 32-byte sector of lead-out:
 constexpr int kRingStride = 2 * kSlotBytes + 16;   // 656 B per lane: 16-B aligned, 2-way bank conflicts at worst
 constexpr int kPieces = kSlotBytes / 16;      // 20 cp.async pieces per slot
 static_assert(kPieces <= 24, "stage_chunk issues at most 3 pieces per lane and polyline");
-constexpr int kWarpSmem = 32 * kRingStride + 32 * 16;   // ring + stream descriptors
+constexpr int kWarpSmem = 32 * kRingStride + 32 * 16 + (TG_STAGE_BULK ? 32 : 0);   // ring + stream descriptors (+ 2 mbarriers in the bulk-copy experiment)
 constexpr int kGroupedSmem = kWarpsPerCta * kWarpSmem;
 
 constexpr int kBins = 2048;                   // bins per queue row
@@ -144,6 +147,19 @@ __device__ __forceinline__ unsigned long long take_ticket(unsigned long long* p)
     unsigned long long old;
     asm volatile("atom.global.add.u64 %0, [%1], 1;" : "=l"(old) : "l"(p) : "memory");
     return old;
+}
+// bulk-copy (TMA, non-tensor) staging primitives of the TG_STAGE_BULK experiment (profiles/experiments/README.md)
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("{ .reg .b64 st; mbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1; }" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("{ .reg .b64 st; mbarrier.arrive.shared::cta.b64 st, [%0]; }" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile("{ .reg .pred p; W: mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1; @!p bra W; }" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -655,6 +671,13 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
     const uint64_t l2_stream = policy_point_reads();
     const uint64_t l2_keep = policy_evict_last();
 
+#if TG_STAGE_BULK
+    const uint32_t bar_u32 = smem_u32(wsm + 32 * kRingStride + 32 * 16);      // two mbarriers, one per ring slot, 32 arrivals each
+    if (lane == 0) { mbar_init(bar_u32, 32); mbar_init(bar_u32 + 8, 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t bar_phase = 0u;                                                  // bit s = parity the next wait on slot s expects
+#endif
     const int64_t M = *queue_len;
     const int64_t n_groups = (M + 31) >> 5;
     const int64_t warps_total = (int64_t)gridDim.x * kWarpsPerCta;
@@ -715,6 +738,32 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
             sd_src[i] = ((uint64_t)d.y << 32) | (uint64_t)d.x;
             sd_len[i] = (int)d.z;
         }
+#if TG_STAGE_BULK
+        // EXPERIMENT: every lane fetches the chunk of ITS OWN polyline with one TMA bulk copy that completes on the slot's
+        // mbarrier.  Source and size are per-lane values, the instruction takes uniform registers: ptxas serialises it
+        // over the lanes (profiles/experiments/README.md).
+        const uint32_t my_ring_u32 = ring_u32 + lane * kRingStride;
+        const uint64_t my_a0 = a0;
+        const int my_total = (int)total;
+        auto stage_chunk = [&](const int q) {
+            const int skip = q > 0 ? 32 : 0;
+            const int pos0 = q * kChunkBytes + skip;
+            const int want = q > 0 ? kChunkBytes : kSlotBytes;
+            const int bytes = min(max(my_total - pos0, 0), want);
+            const uint32_t bar = bar_u32 + 8 * (q & 1);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the slot was last touched through the generic proxy
+            if (bytes > 0) {
+                mbar_arrive_tx(bar, (uint32_t)bytes);
+                bulk_g2s(my_ring_u32 + (q & 1) * kSlotBytes + skip, (const void*)(uintptr_t)(my_a0 + (uint64_t)pos0), (uint32_t)bytes, bar, l2_stream);
+            } else {
+                mbar_arrive(bar);
+            }
+        };
+        auto wait_chunk = [&](const int q) {
+            mbar_wait(bar_u32 + 8 * (q & 1), (bar_phase >> (q & 1)) & 1u);
+            bar_phase ^= 1u << (q & 1);
+        };
+#else
         auto stage_chunk = [&](const int q) {
             const int skip = q > 0 ? 32 : 0;
             const int pos0 = q * kChunkBytes + skip + part * 16;       // byte position in the aligned stream
@@ -732,6 +781,8 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
             }
             cp_async_commit();
         };
+        auto wait_chunk = [&](const int) { cp_async_wait<1>(); };
+#endif
         auto carry_sector = [&](const int q) {                         // end of round q: lead-out of slot q -> head of slot q+1
             const uint4* src = (const uint4*)(my_ring + (q & 1) * kSlotBytes + kChunkBytes);
             uint4* dst = (uint4*)(const_cast<unsigned char*>(my_ring) + ((q + 1) & 1) * kSlotBytes);
@@ -754,8 +805,8 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
             const int rounds_e = (n0 + kChunk - 1) / kChunk;           // rounds that bring in points
 #pragma unroll 1
             for (int q = 0; q < rounds_e; ++q) {
-                if (q + 1 < rounds_e) stage_chunk(q + 1); else cp_async_commit();
-                cp_async_wait<1>();
+                if (q + 1 < rounds_e) stage_chunk(q + 1); else if (!TG_STAGE_BULK) cp_async_commit();
+                wait_chunk(q);
                 __syncwarp();
                 const unsigned char* slot = my_ring + (q & 1) * kSlotBytes + skew;
                 int b = 0;
@@ -799,8 +850,8 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
         } else {
 #pragma unroll 1
             for (int q = 0; q < rounds; ++q) {
-                if (q + 1 < rounds) stage_chunk(q + 1); else cp_async_commit();
-                cp_async_wait<1>();
+                if (q + 1 < rounds) stage_chunk(q + 1); else if (!TG_STAGE_BULK) cp_async_commit();
+                wait_chunk(q);
                 __syncwarp();
                 const unsigned char* slot = my_ring + (q & 1) * kSlotBytes + skew;
 #pragma unroll 1
@@ -831,7 +882,7 @@ k_metrics_grouped(const double* __restrict__ xyz, const uint64_t xyz_lo, const u
                 __syncwarp();
             }
         }
-        cp_async_wait<0>();
+        if (!TG_STAGE_BULK) cp_async_wait<0>();
 
         if (act) {
             // (m0,m1,m2) = P(0) and (cx,cy,cz) = P(n-1) are still in registers
