@@ -25,7 +25,7 @@ PUBLIC_HEADER = os.path.join(ROOT, "include", "tractgeom.h")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-fmad=false",
-    "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default",
+    "--shared", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=default", "-ldl",
 ]
 
 

@@ -11,6 +11,8 @@
 #include "tg_grouped.cuh"
 #include "tractgeom.h"
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges cost nothing unless a profiler (nsys, ncu --nvtx) is attached
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -564,6 +566,12 @@ static int set_err(int code, const char* fmt, const char* a = "", const char* b 
         if (e_ != cudaSuccess) return set_err(TG_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
     } while (0)
 
+// NVTX range over a C-ABI call (the reference has no tracing; nsys/ncu timelines show these names)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 struct DevBuf {
     void* p = nullptr;
     size_t cap = 0;
@@ -852,6 +860,7 @@ static int decode_points(tg_context* c, const void* d_src, int xyz_dtype, int64_
 
 int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const int64_t* d_offsets, int64_t S, int64_t P,
                        double* d_out, uint8_t* d_keep, void* stream) {
+    NvtxRange nvtx_("tg_metrics_csr_dev");
     if (!c) return set_err(TG_E_INVALID, "null context");
     if (S < 0 || P < 0) return set_err(TG_E_INVALID, "negative size");
     if (!dtype_ok(xyz_dtype)) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64, TG_F32, TG_F64_BE or TG_F32_BE");
@@ -872,6 +881,7 @@ int tg_metrics_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const in
 
 static int bundle_reduce_impl(tg_context* c, const double* d_out, const uint8_t* d_keep, const uint8_t* d_select, int64_t S,
                               const int64_t* h_bo, int64_t B, double* d_sums, int64_t* d_counts, double* d_packed, void* stream) {
+    NvtxRange nvtx_("tg_bundle_reduce");
     if (!c) return set_err(TG_E_INVALID, "null context");
     if (S < 0 || B < 0) return set_err(TG_E_INVALID, "negative size");
     if (B == 0) return TG_OK;
@@ -941,6 +951,7 @@ int tg_bundle_spread_dev(tg_context* c, const double* d_out, const uint8_t* d_ke
 
 int tg_resample_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const int64_t* d_offsets, int64_t S, int64_t P,
                         int n_nodes, double* d_nodes, void* stream) {
+    NvtxRange nvtx_("tg_resample_csr_dev");
     if (!c) return set_err(TG_E_INVALID, "null context");
     if (S < 0 || P < 0) return set_err(TG_E_INVALID, "negative size");
     if (n_nodes < 2) return set_err(TG_E_INVALID, "n_nodes must be at least 2");
@@ -972,6 +983,7 @@ int tg_resample_csr_dev(tg_context* c, const void* d_xyz, int xyz_dtype, const i
 
 int tg_resample_csr_host(tg_context* c, const void* h_xyz, int xyz_dtype, const int64_t* h_off, int64_t S, int64_t P,
                          int n_nodes, double* h_nodes) {
+    NvtxRange nvtx_("tg_resample_csr_host");
     if (!c) return set_err(TG_E_INVALID, "null context");
     if (S < 0 || P < 0) return set_err(TG_E_INVALID, "negative size");
     if (n_nodes < 2) return set_err(TG_E_INVALID, "n_nodes must be at least 2");
@@ -1116,6 +1128,7 @@ static void drain_streams(tg_context* c) {
 int tg_metrics_csr_host_ex(tg_context* c, const void* h_xyz, int xyz_dtype, const int64_t* h_off, int64_t S, int64_t P,
                            const int64_t* h_bo, int64_t B, double* h_out, uint8_t* h_keep, double* h_sums, int64_t* h_counts,
                            double* h_spread) {
+    NvtxRange nvtx_("tg_metrics_csr_host_ex");
     if (!c) return set_err(TG_E_INVALID, "null context");
     const int rc = host_pipeline(c, h_xyz, xyz_dtype, h_off, S, P, h_bo, B, h_out, h_keep, h_sums, h_counts, h_spread);
     if (rc != TG_OK) drain_streams(c);
@@ -1276,6 +1289,7 @@ int tg_batch_begin(tg_context* c, int64_t P_cap, int64_t S_cap) {
 }
 
 int tg_batch_push(tg_context* c, const void* h_xyz, int xyz_dtype, int64_t P_i, const int64_t* h_off, int64_t S_i) {
+    NvtxRange nvtx_("tg_batch_push");
     if (!c) return set_err(TG_E_INVALID, "null context");
     if (c->b_Pcap < 0) return set_err(TG_E_INVALID, "tg_batch_push without tg_batch_begin");
     if (!dtype_ok(xyz_dtype)) return set_err(TG_E_INVALID, "xyz_dtype must be TG_F64, TG_F32, TG_F64_BE or TG_F32_BE");
@@ -1327,6 +1341,7 @@ int tg_batch_push(tg_context* c, const void* h_xyz, int xyz_dtype, int64_t P_i, 
 
 int tg_batch_run(tg_context* c, const int64_t* h_bo, int64_t B, double* h_out, uint8_t* h_keep, double* h_sums, int64_t* h_counts,
                  double* h_spread) {
+    NvtxRange nvtx_("tg_batch_run");
     if (!c) return set_err(TG_E_INVALID, "null context");
     if (c->b_Pcap < 0) return set_err(TG_E_INVALID, "tg_batch_run without tg_batch_begin");
     if (B < 0 || (B > 0 && (!h_bo || !h_sums || !h_counts))) return set_err(TG_E_INVALID, "bad bundle argument");

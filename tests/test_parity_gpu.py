@@ -672,3 +672,19 @@ def test_compute_files_streams_a_study_like_the_per_file_calls(gpu_ctx, tmp_path
             row = df_b.iloc[0].to_numpy(float)
             assert n_sl[i] == row[0]
             assert np.allclose(means[i], row[1:], rtol=1e-13, atol=0, equal_nan=True), (i, ms)
+
+
+def test_float32_file_matches_the_float64_contract_not_the_float32_reference(gpu_ctx):
+    """`POINTS n float` data (golden_f32.npz, produced by the unmodified reference): the CUDA path fed the float32 array equals
+    the reference run on the exactly upcast values under the 1e-9 rule; against the reference's literal float32 output it
+    differs by float32 rounding (1e-7 typical, up to ~1e-4 on torsion / bending angle) — the documented deviation."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "golden_f32.npz"))
+    p32, off = z["points32"], z["offsets"]
+    assert p32.dtype == np.float32
+    out, keep = gpu_ctx.metrics_host(p32, off)[:2]
+    assert np.all(keep == 3)
+    assert_table_close(out.T, z["sl64"], "float32 file vs float64 contract")
+    with np.errstate(all="ignore"):
+        rel = np.abs(out.T - z["sl32"]) / np.maximum(np.abs(z["sl32"]), 1e-300)
+    assert 1e-8 < np.nanmax(rel[:, 0]) < 1e-6 and np.nanmax(rel) < 1e-3
