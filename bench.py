@@ -134,7 +134,8 @@ def mem_available_bytes():
 # 0.2 s region holds samples); nvidia-smi as the fallback
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x2: "applications_clocks_setting", 0x10: "sync_boost", 0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
 
     def __init__(self, index):
         self.index = index
