@@ -7,9 +7,8 @@
 //     NaN row at once).  Cutting that order into consecutive GROUPS of 32 gives groups whose members
 //     have the same length (a few per cent straddle a bin boundary).  Polylines of up to
 //     kMaxGroupedN points form one extra row at the head of the queue, longest first (so the longest
-//     groups start first and never form the tail of the launch) — when there are enough of them to
-//     fill the machine; otherwise, and beyond kMaxGroupedN, they are flagged for the one-warp-per-
-//     polyline kernel.
+//     groups start first and never form the tail of the launch); beyond kMaxGroupedN they are flagged
+//     for the one-warp-per-polyline kernel.  The route depends on the polyline's own length only.
 //   * STREAM.  A persistent grid of one 8-warp CTA per SM; every warp is an independent worker
 //     that takes groups round-robin, one polyline per lane, so all 32 lanes run the same number
 //     of iterations — no ragged-length divergence, no halo recomputation, no shuffles.
@@ -25,7 +24,7 @@
 //
 // fp64-pipe budget: the B200 issues ~60 fp64 lane-operations / SM / clock (tools/microbench.cu),
 // and at 25.45 algorithmic bytes per point that roof sits BELOW the HBM roof for this metric set,
-// so the arithmetic is organised to need 95 fp64-pipe instructions per interior point (v1: ~145):
+// so the arithmetic is organised to need 96 fp64-pipe instructions per interior point (v1: ~145):
 //   - every power-of-two scale factor of np.gradient is folded out: the pipeline carries
 //     Vs = 2 v and B = 8 b (exact scalings), so the interior needs no multiplications by 1/2;
 //   - kappa = |B| / (|Vs| + 2e-12)^3 comes from ONE rsqrt of |Vs|^6 |B|^2; the additive epsilon is
