@@ -1259,10 +1259,14 @@ static int batch_grow(tg_context* c, int64_t need_P, int64_t need_S) {
         DevBuf nxyz;
         int rc;
         if ((rc = nxyz.reserve(24 * (size_t)cap + 1024))) return rc;
-        TG_CUDA(cudaStreamSynchronize(c->s_copy));                   // pushed copies have landed; decodes are ordered on the main stream
-        if (c->b_P > 0)
-            TG_CUDA(cudaMemcpyAsync((char*)nxyz.p + 256, (char*)c->d_bxyz.p + 256, 24 * (size_t)c->b_P, cudaMemcpyDeviceToDevice, c->stream));
-        TG_CUDA(cudaStreamSynchronize(c->stream));
+        cudaError_t e = cudaStreamSynchronize(c->s_copy);            // pushed copies have landed; decodes are ordered on the main stream
+        if (e == cudaSuccess && c->b_P > 0)
+            e = cudaMemcpyAsync((char*)nxyz.p + 256, (char*)c->d_bxyz.p + 256, 24 * (size_t)c->b_P, cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) {
+            nxyz.release();
+            return set_err(TG_E_CUDA, "growing the batch failed: %s", cudaGetErrorString(e));
+        }
         c->d_bxyz.release();
         c->d_bxyz = nxyz;
         c->b_Pcap = cap;

@@ -86,3 +86,36 @@ def test_two_rank_gloo_allgather_matches_single_process(tmp_path):
         ref = ref_b.iloc[0].to_numpy(float)
         assert r0["n"][b] == ref[0]                                   # counts bit-exact
         np.testing.assert_allclose(r0["means"][b], ref[1:], rtol=1e-12, atol=0)
+
+
+def test_device_shard_slices_carry_readable_slack():
+    """sharding.DeviceShard (host-side logic, CPU tensors, no context): every slice keeps its polylines' points at
+    points[offsets[s]], carries 4 points of lead (when it is not the first) and 2 of pad, as a view of the global table
+    when the neighbours exist and as a zero-padded copy otherwise; bundle tables are clipped and rebased."""
+    import torch
+    from lesion_condition_vae_b200 import sharding
+    rng = np.random.default_rng(3)
+    n = rng.integers(0, 9, size=200)
+    off = np.concatenate([[0], np.cumsum(n)]).astype(np.int64)
+    pts = rng.normal(size=(int(off[-1]), 3))
+    t_pts, t_off = torch.from_numpy(pts), torch.from_numpy(off)
+    bo = np.array([0, 50, 50, 170, 200], dtype=np.int64)
+    bounds = sharding.shard_ranges(off, 4)
+    covered = 0
+    for r in range(4):
+        for copy in (False, True):
+            sh = sharding.DeviceShard(None, t_pts, t_off, bounds[r], bounds[r + 1], bo, copy=copy)
+            lo, hi = int(bounds[r]), int(bounds[r + 1])
+            assert sh.S == hi - lo and sh.points.shape[0] == sh.P
+            o = sh.offsets.numpy()
+            lead = int(o[0])
+            assert lead == (4 if off[lo] > 0 else 0) and sh.P == lead + int(off[hi] - off[lo]) + 2
+            for s in (0, sh.S // 2, sh.S - 1):
+                if sh.S:
+                    a, b = int(o[s]), int(o[s + 1])
+                    assert np.array_equal(sh.points[a:b].numpy(), pts[off[lo + s]:off[lo + s + 1]])
+            is_view = sh.points.untyped_storage().data_ptr() == t_pts.untyped_storage().data_ptr()
+            assert is_view == (not copy and off[lo] >= lead and off[hi] + 2 <= len(pts))
+            assert np.array_equal(sh.bundle_offsets, np.clip(bo, lo, hi) - lo)
+        covered += hi - lo
+    assert covered == 200
