@@ -107,17 +107,19 @@ def frames_from_table(out, rows, sums, counts, spread=None):
     if n_rows == 0:
         # ref:189,197: pd.DataFrame([]) has no columns, df_sl["length"] raises KeyError('length')
         raise KeyError("length")
-    idx = np.flatnonzero(rows)
-    df_sl = pd.DataFrame({name: out[m, idx] for m, name in enumerate(SL_COLUMNS)})
+    # one (rows, 17) float64 block that the frame owns (3x cheaper to build than 17 column arrays: at 1,000 polylines the
+    # frames used to cost more than the device call)
+    table = out.T.copy() if rows.all() else np.ascontiguousarray(out[:, rows].T)
+    df_sl = pd.DataFrame(table, columns=list(SL_COLUMNS), copy=False)
     with np.errstate(invalid="ignore", divide="ignore"):
         means = np.where(counts[1:] > 0, sums / np.maximum(counts[1:], 1), np.nan)
-    bundle = {"n_streamlines": n_rows}
+    bundle = {"n_streamlines": np.array([n_rows], dtype=np.int64)}
     for name, v in zip(BUNDLE_COLUMNS[1:], means):
-        bundle[name] = float(v)
+        bundle[name] = np.array([v], dtype=np.float64)
     if spread is not None:
         for name, v in zip(SPREAD_COLUMNS, np.asarray(spread, dtype=np.float64).reshape(-1)):
-            bundle[name] = float(v)
-    return df_sl, pd.DataFrame([bundle])
+            bundle[name] = np.array([v], dtype=np.float64)
+    return df_sl, pd.DataFrame(bundle)
 
 
 def compute_streamline_metrics_csr(points, offsets, max_streamlines: Optional[int] = None, ctx=None, extra_stats=False):
