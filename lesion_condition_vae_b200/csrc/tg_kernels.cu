@@ -5,8 +5,15 @@
 //            k_metrics_long   polylines too long for the queue bins: one warp per polyline.
 // Kernel 2a k_bundle_tiles    per-tile partial moments of the 13 aggregated columns (tiles never
 //                             straddle a bundle boundary) — ref:191-210 of tract_geom_proc.py.
-// Kernel 2b k_bundle_final    one warp per bundle adds its tiles' partials in tile order, so the
-//                             result does not depend on scheduling.
+// Kernel 2b k_bundle_final    one CTA per bundle adds its tiles' partials in a fixed order, so the
+//                             result does not depend on scheduling; optionally as ONE row of 27 doubles
+//                             {13 sums | kept rows | 13 non-NaN counts}: the multi-GPU all-gather payload.
+// Kernel 0  k_decode_points   point storage other than native float64 (float32; the big-endian float32 /
+//                             float64 of a binary VTK file) -> float64, exactly, at HBM speed.
+// Kernel 3  k_spread_*        opt-in np.nanstd / nanmin / nanmax of the bundle columns.
+// Kernel 4  k_resample        arc-length resampling to K nodes (N4), a polyline staged by ONE TMA bulk copy.
+// Host      tg_metrics_csr_host: chunked H2D || kernels || D2H; tg_batch_*: files pushed as they are parsed,
+//           one device call per batch; tg_vtk_* / tg_parse_ascii_*: ingest helpers (no device).
 #include "tg_device.cuh"
 #include "tg_grouped.cuh"
 #include "tractgeom.h"
