@@ -274,3 +274,20 @@ def test_select_prefix_matches_the_reference_loader_rule():
                 got = td.select_prefix(view, off, ms).tolist()
                 if ref is not None:
                     assert got == ref, (trial, ms)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside ours) emits one JSON line with the contract keys,
+    the same metric / unit as the GPU arm, a cpu_baseline describing the run and a zero-copy e2e record."""
+    import json
+    import sys
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0", "--config", "0"],
+                         capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["metric"] == "streamlines_per_sec" and line["unit"] == "streamlines/s"
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] and "workload" in line["config"]
